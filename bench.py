@@ -1,0 +1,284 @@
+"""bench.py -- optimizer steps/s of the DotaClient optimizer hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c1]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+A "step" is one ``DotaOptimizer.train()`` call (forward, PPO loss, backward, gradient all-reduce, clip, Adam)
+on one synthetic experience batch.  Default workload = BASELINE.json configs[1] ("c2": batch 256 x seq 512,
+hidden 128, LSTM) PER GPU (weak scaling); ``value`` counts one such batch per GPU per step.
+
+Keys: value (inputs resident in HBM), e2e (inputs in pinned host memory, H2D + result D2H inside the timed
+region), roofline (recurrence fwd+bwd kernels: algorithmic bytes / CUDA-event time / measured HBM peak),
+cpu_baseline (the oracle port of the reference's train() on the host cores, bounded sample), clocks,
+gpu_launches.  ``--impl reference`` times the reference's CPU implementation (oracle port; the reference is
+pure Python + torch CPU and cannot travel to the GPU box) on the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CONFIGS = {                       # BASELINE.json configs; batch is PER GPU
+    "c1": dict(batch=1, seq_len=64, hidden=128, cell="lstm"),
+    "c2": dict(batch=256, seq_len=512, hidden=128, cell="lstm"),
+    "c3": dict(batch=512, seq_len=512, hidden=256, cell="lstm"),
+    "c4": dict(batch=512, seq_len=1024, hidden=512, cell="lstm"),
+}
+FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--config", choices=sorted(CONFIGS), default="c2")
+    p.add_argument("--cell", choices=["gru", "lstm"], default=None)
+    p.add_argument("--batch", type=int, default=None)
+    p.add_argument("--seq-len", type=int, default=None)
+    p.add_argument("--hidden", type=int, default=None)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def resolve_config(args):
+    cfg = dict(CONFIGS[args.config])
+    for k, a in (("batch", args.batch), ("seq_len", args.seq_len), ("hidden", args.hidden), ("cell", args.cell)):
+        if a is not None:
+            cfg[k] = a
+    return cfg
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_steps_per_sec(cfg, budget_s=20.0, threads=None):
+    """The oracle port of the reference's ``DotaOptimizer.train`` (optimizer.py:581-689) on the host cores.
+
+    Bounded sample: a batch of ``b`` sequences of the config's seq_len/hidden/cell chosen so that one step takes a
+    few seconds; steps/s for the full batch is extrapolated linearly in the batch size (the work is per-token).
+    """
+    import torch
+    from oracle import ref_optimizer as RO
+    from oracle.ref_policy import RefPolicy
+    from dotaclient_b200.synthetic import make_rollout
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, H, cell, B = cfg["seq_len"], cfg["hidden"], cfg["cell"], cfg["batch"]
+    b = max(1, min(B, max(1, 8192 // S)))                 # ~8k tokens per sample step
+    torch.manual_seed(7)
+    opt = RO.RefOptimizer(RefPolicy(H, cell), seq_len=S)
+    seqs = []
+    for i in range(b):
+        seqs.extend(opt.experiences_from_rollout(make_rollout(S, 7 + i)))
+    opt.train(seqs)                                        # warm-up
+    t0, n = time.perf_counter(), 0
+    while True:
+        opt.train(seqs)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 20:
+            break
+    sample_steps_per_s = n / el
+    full = sample_steps_per_s * b / B
+    sample = "oracle port of optimizer.py:581-689, batch %d x seq %d (hidden %d, %s), %d steps in %.1f s; scaled x%d/%d to batch %d" % (
+        b, S, H, cell, n, el, b, B, B)
+    return full, cores, sample
+
+
+def run_reference_arm(args, cfg):
+    """``--impl reference``: the reference's CPU train() (oracle port) on all host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps_per_s_samples = []
+    cores, sample = os.cpu_count() or 1, ""
+    per = max(3.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=per)
+        if i >= args.warmup:
+            steps_per_s_samples.append(v)
+    value = sum(steps_per_s_samples) / len(steps_per_s_samples)
+    line = {
+        "impl": "reference", "metric": "optimizer_steps_per_sec", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args.gpus, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU data-parallel ranks of the reference run the same per-rank batch concurrently; one host, so N>1 is not faster",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cfg, n_gpus, where):
+    return {"workload": "BASELINE configs: synthetic experience batch=%d seq=%d hidden=%d per GPU, %s cell; "
+                        "one DotaOptimizer.train() per step" % (cfg["batch"], cfg["seq_len"], cfg["hidden"], cfg["cell"]),
+            "batch_per_gpu": cfg["batch"], "global_batch": cfg["batch"] * n_gpus, "seq_len": cfg["seq_len"],
+            "hidden": cfg["hidden"], "cell": cfg["cell"], "parallelism": "dp%d" % n_gpus,
+            "l2": "per-step inputs exceed the 126 MB L2" if cfg["batch"] * cfg["seq_len"] * 2100 > 126e6
+                  else "L2 flushed between steps", "where": where}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse_args()
+    cfg = resolve_config(args)
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+    import torch
+    import torch.distributed as dist
+    from dotaclient_b200 import ops
+    from dotaclient_b200.optimizer import DotaOptimizer, ExperienceBatch
+    from dotaclient_b200.synthetic import make_rollout, rollout_seed
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl")
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    dev = torch.device("cuda", local_rank)
+    B, S, H, cell = cfg["batch"], cfg["seq_len"], cfg["hidden"], cfg["cell"]
+
+    opt = DotaOptimizer(rmq_host="bench", rmq_port=rank, epochs=1, min_seq_per_epoch=B, seq_len=S, learning_rate=5e-5,
+                        checkpoint=False, pretrained_model=None, mq_prefetch_count=1, log_dir=tempfile.mkdtemp(),
+                        entropy_coef=5e-4, vf_coef=0.5, run_local=True, hidden_size=H, cell=cell)
+    # synthetic experience: B rollouts of exactly S steps per rank, prepared by the product's own
+    # experiences_from_rollout (old log-probs, values, GAE under the current weights), then stacked once.
+    seqs = []
+    with torch.no_grad():
+        for i in range(B):
+            seqs.extend(opt.experiences_from_rollout(make_rollout(S, rollout_seed(rank, i))))
+    batch_dev = ExperienceBatch.from_sequences(seqs, dev)
+    del seqs
+    batch_host = batch_dev.pin_memory()
+    h2d_bytes = batch_host.nbytes()
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    step_dev = lambda: opt.train(batch_dev)          # noqa: E731
+    step_e2e = lambda: opt.train(batch_host)         # noqa: E731
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE.reset(enabled=True)
+    ms_total = timed(step_dev, args.steps)
+    prof = ops.PROFILE.summary(args.steps)
+    launches = ops.PROFILE.launches
+    ops.PROFILE.reset(enabled=False)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = ms_total / args.steps
+    value = world * 1000.0 / ms_per_step
+    e2e_value = world * 1000.0 / (ms_e2e / args.steps)
+    tokens = B * S
+    G = 4 if cell == "lstm" else 3
+    peak, peak_src = measured_peak_hbm()
+    rnn_ms = prof.get("rnn_fwd", 0.0) + prof.get("rnn_bwd", 0.0)        # average per step, CUDA events on the launch stream
+    rnn_bytes = 12.0 * tokens * (G + 1) * H                             # fwd 4N(G+1)H + bwd 8N(G+1)H
+    achieved = rnn_bytes / (rnn_ms * 1e-3) / 1e9 if rnn_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_step": rnn_bytes, "kernel_ms_per_step": rnn_ms,
+                "share_of_step": rnn_ms / ms_per_step, "peak_source": peak_src,
+                "dependency_floor_note": "2*S=%d strictly sequential recurrence steps per optimizer step" % (2 * S),
+                "kernels_ms_per_step": prof}
+    line = {
+        "metric": "optimizer_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, world, "hbm"),
+        "env_steps_per_sec": value * tokens,
+        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 80,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=20.0)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""One flat fp32 buffer for all parameters, one for all gradients (+ per-parameter has-grad slots).
+
+The reference synchronises gradients with 68 blocking collectives per step (``distributed.py:29-57``)
+and then walks the 34 tensors three more times (two norm passes, clip, Adam: ``optimizer.py:674-681``).
+Re-homing every ``nn.Parameter`` as a view into one contiguous buffer turns that into ONE all-reduce
+over NVLink and one fused finish kernel (``csrc/grad_finish.cu``).  ``state_dict()`` is unaffected
+(same keys, shapes, values), so checkpoints stay byte-compatible with the reference's agents.
+"""
+import torch
+
+# Parameters that only receive a gradient when a particular action head was used in the batch
+# (``optimizer.py:627-630`` skips unused heads, so their .grad stays None in the reference):
+# affine_unit_eth reaches the loss only through the target_unit head because of the
+# ``eth_embedding_max`` quirk at ``policy.py:127``.
+HEAD_INDEX = {"enum": 0, "x": 1, "y": 2, "target_unit": 3, "ability": 4}
+VALUE_SLOT = 5     # pseudo-head: 1 when vf_coef > 0 (value loss present), else 0
+PARAM_HEAD = {
+    "affine_head_enum": 0, "affine_move_x": 1, "affine_move_y": 2,
+    "affine_unit_attention": 3, "affine_unit_eth": 3, "affine_head_ability": 4,
+    "affine_value": VALUE_SLOT,
+}
+
+
+def head_dependency(param_name):
+    """-1 if the parameter always has a gradient, else the index of the head it depends on."""
+    return PARAM_HEAD.get(param_name.split(".")[0], -1)
+
+
+class FlatParameterSpace:
+    """Re-homes ``module``'s parameters (in ``named_parameters()`` order == the reference's all-reduce order)."""
+
+    def __init__(self, module, device=None):
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("module has no trainable parameters")
+        device = torch.device(device) if device is not None else named[0][1].device
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        sizes = [p.numel() for p in self.params]
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        self.total = offs[-1]
+        self.n_seg = len(sizes)
+        self.offsets = offs
+        self.param = torch.empty(self.total, dtype=torch.float32, device=device)
+        # gradient buffer carries n_seg extra slots: per-parameter has-grad flags / counts (distributed.py:36-37)
+        self.grad_full = torch.zeros(self.total + self.n_seg, dtype=torch.float32, device=device)
+        self.grad = self.grad_full[:self.total]
+        self.flags = self.grad_full[self.total:]
+        for p, lo, hi in zip(self.params, offs[:-1], offs[1:]):
+            self.param[lo:hi].copy_(p.data.reshape(-1))
+            p.data = self.param[lo:hi].view(p.shape)
+            p.grad = self.grad[lo:hi].view(p.shape)
+        self.seg_off = torch.tensor(offs, dtype=torch.int64, device=device)
+        self.seg_head = torch.tensor([head_dependency(n) for n in self.names], dtype=torch.int32, device=device)
+        module._dc_flat_space = self
+
+    @staticmethod
+    def of(module, device=None):
+        space = getattr(module, "_dc_flat_space", None)
+        if space is None or (device is not None and space.param.device != torch.device(device)):
+            space = FlatParameterSpace(module, device)
+        return space
+
+    def rebind(self):
+        """Re-attach ``.grad`` views (``optimizer.zero_grad()`` / ``set_to_none`` detaches them)."""
+        for p, lo, hi in zip(self.params, self.offsets[:-1], self.offsets[1:]):
+            if p.grad is None or p.grad.data_ptr() != self.grad[lo:hi].data_ptr():
+                p.grad = self.grad[lo:hi].view(p.shape)
+
+    def zero_grad(self):
+        self.grad_full.zero_()
+        self.rebind()
+
+    def grad_of(self, name):
+        i = self.names.index(name)
+        return self.grad[self.offsets[i]:self.offsets[i + 1]].view(self.params[i].shape)

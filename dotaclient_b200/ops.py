@@ -1,0 +1,309 @@
+"""Torch-facing wrappers of the C-ABI kernels (device memory + stream plumbing only).
+
+Every function here requires CUDA tensors and enqueues hand-written sm_100a kernels from
+``libdotaclient_b200.so`` on torch's current stream.  No CPU path exists: CPU tensors raise.
+"""
+import os
+
+import torch
+
+from . import _lib
+
+CELL_ID = {"gru": 0, "lstm": 1}
+HEAD_KEYS = ("enum", "x", "y", "target_unit", "ability")     # policy.py:46
+HEAD_SIZES = (4, 9, 9, 40, 3)
+GATES = {"gru": 3, "lstm": 4}
+
+
+class _Profile:
+    """Optional per-kernel CUDA-event timing on the launching stream + a count of OUR kernel launches.
+
+    Used by bench.py (roofline) -- events are recorded around each C-ABI call on torch's current stream.
+    """
+
+    def __init__(self):
+        self.reset(False)
+
+    def reset(self, enabled=False):
+        self.enabled = enabled
+        self.pairs = []
+        self.launches = 0
+
+    class _Span:
+        def __init__(self, prof, name, n_launches):
+            self.prof, self.name, self.n = prof, name, n_launches
+
+        def __enter__(self):
+            if self.prof.enabled:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.prof.enabled:
+                self.e1.record()
+                self.prof.pairs.append((self.name, self.e0, self.e1))
+                self.prof.launches += self.n
+            return False
+
+    def span(self, name, n_launches):
+        return _Profile._Span(self, name, n_launches)
+
+    def totals(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in self.pairs:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def summary(self, steps=None):
+        """ms per kernel name, averaged per step when ``steps`` is given (else per call)."""
+        tot = self.totals()
+        if steps:
+            return {k: v / steps for k, v in tot.items()}
+        counts = {}
+        for name, _, _ in self.pairs:
+            counts[name] = counts.get(name, 0) + 1
+        return {k: v / counts[k] for k, v in tot.items()}
+
+
+PROFILE = _Profile()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dotaclient_b200 kernels need CUDA tensors (no CPU fallback); got %s" % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+def _u8(t):
+    """bool/uint8 tensor -> contiguous byte view (0/1)."""
+    t = t.contiguous()
+    if t.dtype == torch.bool:
+        return t.view(torch.uint8)
+    if t.dtype != torch.uint8:
+        t = (t != 0).view(torch.uint8)
+    return t
+
+
+# --------------------------------------------------------------------------------------------- GAE
+def gae_scan(rewards, values, seg_off, gamma=0.98, lam=0.97, boot_value=None, boot_reward=None):
+    """GAE advantages + rewards-to-go for many rollouts (``optimizer.py:53-64,397,417-421``).
+
+    rewards [n_rows] or [n_rows, n_sub] fp32; values [n_rows]; seg_off int64 [n_seg+1] (device).
+    """
+    _need_cuda(rewards, values, seg_off)
+    rewards, values = _f32c(rewards), _f32c(values)
+    n_sub = 1 if rewards.dim() == 1 else rewards.shape[1]
+    n_rows = values.numel()
+    assert rewards.numel() == n_rows * n_sub
+    seg_off = seg_off.to(torch.int64).contiguous()
+    adv = torch.empty(n_rows, dtype=torch.float32, device=values.device)
+    ret = torch.empty_like(adv)
+    lib = _lib.load()
+    with PROFILE.span("gae_scan", 1):
+        _lib.check(lib.dc_gae_scan(rewards.data_ptr(), n_sub, values.data_ptr(), seg_off.data_ptr(),
+                                   seg_off.numel() - 1, _lib.ptr(boot_value), _lib.ptr(boot_reward), float(gamma),
+                                   float(lam), adv.data_ptr(), ret.data_ptr(), _lib.stream_ptr()), "dc_gae_scan")
+    return adv, ret
+
+
+# --------------------------------------------------------------------------------------------- RNN
+_workspaces = {}
+
+
+def _rnn_workspace(cell, H, device):
+    key = (cell, H, device)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = _lib.load().dc_rnn_workspace_bytes(CELL_ID[cell], H)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _i2h_matmul_context():
+    """The input-to-hidden GEMM is the one dense contraction that may use tensor cores (TF32)."""
+    return os.environ.get("DOTACLIENT_B200_I2H_TF32", "0") == "1"
+
+
+def _rnn_forward_impl(x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
+    """i2h GEMM (cuBLAS) + recurrence kernel.  Returns (x2, w_ih, w_hh, gates, ybuf, cbuf)."""
+    _need_cuda(x, w_ih, w_hh, b_ih, b_hh, h0, c0)
+    S, B, Hin = x.shape
+    H = w_hh.shape[1]
+    N = S * B
+    x2 = _f32c(x.detach()).view(N, Hin)
+    w_ih, w_hh, b_ih, b_hh = _f32c(w_ih.detach()), _f32c(w_hh.detach()), _f32c(b_ih.detach()), _f32c(b_hh.detach())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = _i2h_matmul_context()
+    try:
+        gates = torch.addmm(b_ih, x2, w_ih.t())          # [N, G*H] = x W_ih^T + b_ih
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    ybuf = torch.empty((S + 1, B, H), dtype=torch.float32, device=x.device)
+    cbuf = torch.empty((S + 1, B, H), dtype=torch.float32, device=x.device)
+    ybuf[0].copy_(h0.detach().reshape(B, H))
+    if cell == "lstm":
+        cbuf[0].copy_(c0.detach().reshape(B, H))
+    ws = _rnn_workspace(cell, H, x.device)
+    lib = _lib.load()
+    with PROFILE.span("rnn_fwd", 1):
+        _lib.check(lib.dc_rnn_seq_fwd(CELL_ID[cell], gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
+                                      ybuf.data_ptr(), cbuf.data_ptr(), B, S, H, ws.data_ptr(), _lib.stream_ptr()),
+                   "dc_rnn_seq_fwd")
+    return x2, w_ih, w_hh, gates, ybuf, cbuf
+
+
+def rnn_forward_states(x_tm, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
+    """No-grad forward returning the full state buffers: ybuf [S+1,B,H] (slot 0 = h0, slot t+1 = h_t) and
+    cbuf [S+1,B,H] (LSTM cell states).  Used by experience prep to read the hidden state at chunk boundaries."""
+    with torch.no_grad():
+        _, _, _, _, ybuf, cbuf = _rnn_forward_impl(x_tm, w_ih, w_hh, b_ih, b_hh, h0, c0, cell)
+    return ybuf, cbuf
+
+
+class RnnSequence(torch.autograd.Function):
+    """Time-major GRU/LSTM layer: i2h GEMM (cuBLAS) + hand-written recurrence kernels.
+
+    forward(x [S,B,Hin], w_ih [G*H,Hin], w_hh [G*H,H], b_ih, b_hh, h0 [B,H], c0 [B,H]|None, cell)
+      -> y [S,B,H], h_n [B,H], c_n [B,H] (zeros-size-0 tensor for GRU)
+    Semantics of ``torch.nn.GRU/LSTM(batch_first=...)`` as used in ``policy.py:66,141``.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
+        S, B, Hin = x.shape
+        H = w_hh.shape[1]
+        x2, w_ih, w_hh, gates, ybuf, cbuf = _rnn_forward_impl(x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell)
+        ctx.cell, ctx.dims = cell, (S, B, Hin, H, GATES[cell])
+        ctx.save_for_backward(x2, w_ih, w_hh, gates, ybuf, cbuf)
+        y = ybuf[1:]
+        h_n = ybuf[S].clone()
+        if cell == "lstm":
+            c_n = cbuf[S].clone()
+        else:
+            c_n = ybuf.new_empty(0)
+            ctx.mark_non_differentiable(c_n)
+        return y, h_n, c_n
+
+    @staticmethod
+    def backward(ctx, dy, dhn, dcn):
+        x2, w_ih, w_hh, gates, ybuf, cbuf = ctx.saved_tensors
+        cell = ctx.cell
+        S, B, Hin, H, G = ctx.dims
+        N = S * B
+        if getattr(ctx, "_consumed", False):
+            raise RuntimeError("RnnSequence backward ran twice: the saved gate buffer is consumed in place")
+        ctx._consumed = True
+        dy = _f32c(dy) if dy is not None else torch.zeros((S, B, H), dtype=torch.float32, device=x2.device)
+        dhn = _f32c(dhn) if dhn is not None else None
+        dcn = _f32c(dcn) if (dcn is not None and cell == "lstm" and dcn.numel()) else None
+        dh0 = torch.empty((B, H), dtype=torch.float32, device=x2.device)
+        dc0 = torch.empty((B, H), dtype=torch.float32, device=x2.device) if cell == "lstm" else None
+        ws = _rnn_workspace(cell, H, x2.device)
+        lib = _lib.load()
+        with PROFILE.span("rnn_bwd", 1):
+            _lib.check(lib.dc_rnn_seq_bwd(CELL_ID[cell], gates.data_ptr(), w_hh.data_ptr(), ybuf.data_ptr(),
+                                          cbuf.data_ptr(), dy.data_ptr(), _lib.ptr(dhn), _lib.ptr(dcn), dh0.data_ptr(),
+                                          _lib.ptr(dc0), B, S, H, ws.data_ptr(), _lib.stream_ptr()), "dc_rnn_seq_bwd")
+        dgi = gates                                   # [N, G*H], overwritten in place by the kernel
+        hprev = ybuf[:S].view(N, H)                   # h_{t-1} for every token (slot t)
+        tf32 = _i2h_matmul_context()
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            dx = torch.mm(dgi, w_ih).view(S, B, Hin) if ctx.needs_input_grad[0] else None
+            dw_ih = torch.mm(dgi.t(), x2)
+            db_ih = dgi.sum(0)
+            if cell == "lstm":
+                dw_hh = torch.mm(dgi.t(), hprev)
+                db_hh = db_ih
+            else:
+                dghn = cbuf[1:].view(N, H)            # n-gate part of dgh (= dgi_n * r)
+                dw_hh = torch.empty_like(w_hh)
+                torch.mm(dgi[:, :2 * H].t(), hprev, out=dw_hh[:2 * H])
+                torch.mm(dghn.t(), hprev, out=dw_hh[2 * H:])
+                db_hh = torch.cat([db_ih[:2 * H], dghn.sum(0)])
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        return dx, dw_ih, dw_hh, db_ih, db_hh, dh0, dc0, None
+
+
+def rnn_sequence(x_tm, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
+    return RnnSequence.apply(x_tm, w_ih, w_hh, b_ih, b_hh, h0, c0, cell)
+
+
+# --------------------------------------------------------------------------------------------- PPO loss
+def ppo_loss_fwd_bwd(logits, masks, actions, old_logp, adv_raw, ret, value, e_clip, entropy_coef, vf_coef):
+    """Fused PPO loss + gradients (``optimizer.py:587-589,621-665`` and their backward).
+
+    logits/masks/actions: sequences of 5 tensors [..., n_h] in HEAD_KEYS order (any leading dims,
+    same token order everywhere); old_logp [..., 5]; adv_raw/ret/value [...].
+    Returns (out[16] fp32, n_actions[5] int32, dlogits list, dvalue) -- all on device, no sync.
+    """
+    logits = [_f32c(l.detach()) for l in logits]
+    _need_cuda(*logits)
+    N = logits[0].numel() // HEAD_SIZES[0]
+    masks = [_u8(m) for m in masks]
+    actions = [_u8(a) for a in actions]
+    for h in range(5):
+        assert logits[h].numel() == N * HEAD_SIZES[h] and masks[h].numel() == N * HEAD_SIZES[h] \
+            and actions[h].numel() == N * HEAD_SIZES[h], "head %d shape mismatch" % h
+    old_logp, adv_raw, ret, value = _f32c(old_logp), _f32c(adv_raw), _f32c(ret), _f32c(value.detach())
+    assert old_logp.numel() == N * 5 and adv_raw.numel() == N and ret.numel() == N and value.numel() == N
+    dev = logits[0].device
+    dlogits = [torch.empty_like(l) for l in logits]
+    dvalue = torch.empty_like(value)
+    out = torch.empty(_lib.LOSS_SLOTS, dtype=torch.float32, device=dev)
+    n_actions = torch.empty(5, dtype=torch.int32, device=dev)
+    ws = torch.empty(_lib.PPO_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+    lib = _lib.load()
+    with PROFILE.span("ppo_loss", 2):
+        _lib.check(lib.dc_ppo_loss_fwd_bwd(_lib.ptr5(logits), _lib.ptr5(masks), _lib.ptr5(actions),
+                                           old_logp.data_ptr(), adv_raw.data_ptr(), ret.data_ptr(), value.data_ptr(),
+                                           N, float(e_clip), float(entropy_coef), float(vf_coef), _lib.ptr5(dlogits),
+                                           dvalue.data_ptr(), out.data_ptr(), n_actions.data_ptr(), ws.data_ptr(),
+                                           _lib.stream_ptr()), "dc_ppo_loss_fwd_bwd")
+    return out, n_actions, dlogits, dvalue
+
+
+def selected_logp(logits, masks, actions):
+    """Dense [N,5] log-prob of the taken action per head (0 where none) -- ``optimizer.py:387-390``."""
+    logits = [_f32c(l.detach()) for l in logits]
+    _need_cuda(*logits)
+    N = logits[0].numel() // HEAD_SIZES[0]
+    masks = [_u8(m) for m in masks]
+    actions = [_u8(a) for a in actions]
+    out = torch.empty((N, 5), dtype=torch.float32, device=logits[0].device)
+    lib = _lib.load()
+    with PROFILE.span("selected_logp", 1):
+        _lib.check(lib.dc_selected_logp(_lib.ptr5(logits), _lib.ptr5(masks), _lib.ptr5(actions), N, out.data_ptr(),
+                                        _lib.stream_ptr()), "dc_selected_logp")
+    return out
+
+
+# --------------------------------------------------------------------------------------------- grad finish
+def grad_flags(flat_grad, total, seg_head, n_actions):
+    lib = _lib.load()
+    with PROFILE.span("grad_flags", 1):
+        _lib.check(lib.dc_grad_flags(flat_grad.data_ptr(), total, seg_head.data_ptr(), seg_head.numel(),
+                                     n_actions.data_ptr(), _lib.stream_ptr()), "dc_grad_flags")
+
+
+def grad_finish(flat_param, flat_grad, exp_avg, exp_avg_sq, steps, seg_off, seg_head, total, lr, betas, eps,
+                max_norm, loss_out, metrics, workspace):
+    lib = _lib.load()
+    with PROFILE.span("grad_finish", 3):
+        _lib.check(lib.dc_grad_finish(flat_param.data_ptr(), flat_grad.data_ptr(), exp_avg.data_ptr(),
+                                      exp_avg_sq.data_ptr(), steps.data_ptr(), seg_off.data_ptr(), seg_head.data_ptr(),
+                                      seg_head.numel(), total, float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                      float(max_norm), _lib.ptr(loss_out), metrics.data_ptr(), workspace.data_ptr(),
+                                      _lib.stream_ptr()), "dc_grad_finish")

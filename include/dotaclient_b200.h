@@ -1,0 +1,145 @@
+/* dotaclient_b200 -- C-ABI of the B200-native DotaClient optimizer hot path.
+ *
+ * The reference (TimZaman/dotaclient @ 8615b90) is pure Python on torch CPU; it has no FFI
+ * layer.  Each entry point below replaces a stock-torch/scipy op sequence of the reference's
+ * optimizer step and names it (file:line in the reference tree).  A maintainer binds these
+ * with ctypes from optimizer.py / policy.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless stated), owned by the caller; nothing is
+ *     allocated or freed by the library, nothing is synchronised: work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - return value: 0 = ok; >0 = cudaError_t; <0 = argument error (DC_EINVAL ...).
+ *     dc_last_error() returns a thread-local human-readable message for the last failure.
+ *   - bool tensors (masks / actions) are bytes holding 0 or 1 (torch.bool layout).
+ *   - "time-major" = [S, B, ...]: token (t, b) lives at row t*B + b.
+ *   - compiled for sm_100a only; there is no CPU fallback.
+ */
+#ifndef DOTACLIENT_B200_H
+#define DOTACLIENT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DC_OK 0
+#define DC_EINVAL (-1)      /* bad argument */
+#define DC_EUNSUPPORTED (-2) /* shape outside what the kernels are built for */
+
+#define DC_CELL_GRU 0  /* gate order r,z,n  (torch.nn.GRU,  policy.py:66) */
+#define DC_CELL_LSTM 1 /* gate order i,f,g,o (torch.nn.LSTM; the cell BASELINE.json names) */
+
+#define DC_NUM_HEADS 5    /* enum,x,y,target_unit,ability  (policy.py:46) */
+#define DC_LOSS_SLOTS 16  /* layout of the `out` vector of dc_ppo_loss_fwd_bwd, see below */
+
+typedef void *dc_stream_t;
+
+/* Library / device introspection. */
+int dc_version(void);
+const char *dc_last_error(void);
+/* sm count, compute capability of the current device; >0 cudaError_t if there is none. */
+int dc_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- GAE -----------------------------------------------------------------------------
+ * Replaces advantage_returns()/discount() (optimizer.py:53-64) and the reward reduction that
+ * feeds them (optimizer.py:397,417-421) for n_seg rollouts at once.
+ *   rewards  [n_rows, n_sub]   sub-rewards per step (n_sub = 10, policy.py:20) or n_sub = 1
+ *   values   [n_rows]          critic values (padded steps included, optimizer.py:396)
+ *   seg_off  [n_seg+1] int64   rollout r covers rows seg_off[r] .. seg_off[r+1]-1
+ *   boot_value [n_seg] or NULL value of the state after the last row   } the trailing elements the
+ *   boot_reward[n_seg] or NULL start of the rewards-to-go recursion    } reference appends, both 0
+ *                              (NULL = 0: terminated rollouts, optimizer.py:413-420)
+ *   adv, ret [n_rows]          outputs
+ * deltas in fp32, the two reverse scans accumulate in float64 and round to fp32 exactly like
+ * scipy.signal.lfilter + astype(float32) does.  Warp-shuffle segmented scan, one warp / rollout.
+ */
+int dc_gae_scan(const float *rewards, int n_sub, const float *values, const int64_t *seg_off,
+                int n_seg, const float *boot_value, const float *boot_reward, double gamma,
+                double lam, float *adv, float *ret, dc_stream_t stream);
+
+/* ---- recurrent core --------------------------------------------------------------------
+ * Replaces the time recurrence inside nn.GRU / nn.LSTM (policy.py:66,141) -- forward and
+ * backward -- given the input-to-hidden pre-activations of all steps.
+ *
+ * Forward
+ *   gates  [S, B, G, H] in : x_t W_ih^T + b_ih (time-major)      G = 3 (GRU) / 4 (LSTM)
+ *                       out: activated gates (r,z,n | i,f,g,o), saved for backward (in place)
+ *   w_hh   [G*H, H], b_hh [G*H]   rnn.weight_hh_l0 / rnn.bias_hh_l0
+ *   ybuf   [S+1, B, H]  slot 0 = h_0 (in), slot t+1 = h_t (out)   -> y = ybuf[1:], h_n = ybuf[S]
+ *   cbuf   [S+1, B, H]  LSTM: slot 0 = c_0 (in), slot t+1 = c_t (out)
+ *                       GRU : slot t+1 = W_hn h_{t-1} + b_hn (out, saved for backward)
+ *   workspace: dc_rnn_workspace_bytes(cell, H) bytes of scratch.
+ * Backward (consumes what forward left behind)
+ *   gates  in: activated gates   out: dL/d(gates pre-activation wrt the i2h branch) = dgi
+ *   cbuf   LSTM: unchanged.  GRU: slot t+1 out = dL/d(W_hn h + b_hn) (the n-gate part of dgh)
+ *   dy     [S, B, H]  dL/dy (time-major); dhn/dcn [B, H] or NULL (gradient of the final state)
+ *   dh0/dc0 [B, H] or NULL outputs.
+ */
+size_t dc_rnn_workspace_bytes(int cell, int H);
+int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const float *b_hh, float *ybuf,
+                   float *cbuf, int B, int S, int H, void *workspace, dc_stream_t stream);
+int dc_rnn_seq_bwd(int cell, float *gates, const float *w_hh, const float *ybuf, float *cbuf,
+                   const float *dy, const float *dhn, const float *dcn, float *dh0, float *dc0,
+                   int B, int S, int H, void *workspace, dc_stream_t stream);
+
+/* ---- fused PPO loss + gradient ----------------------------------------------------------
+ * Replaces optimizer.py:587-589 (advantage normalisation) and :621-665 (masked log-softmax x5,
+ * ratio, clipped surrogate, entropy, value loss) AND their autograd backward, for N tokens.
+ *   logits[h]  [N, n_h] fp32   n_h = 4,9,9,40,3     masks[h], actions[h] [N, n_h] bytes
+ *   old_logp   [N, 5]   log-prob of the taken action per head at prep time (dense form of
+ *                       Sequence.log_probs_sel, optimizer.py:387-390); ignored where no action
+ *   adv_raw, ret, value [N]
+ *   dlogits[h] [N, n_h], dvalue [N]   gradients of the total loss (loss.backward(), :672)
+ *   out [DC_LOSS_SLOTS] fp32: 0 loss, 1 policy_loss, 2 entropy_loss, 3 value_loss,
+ *       4..8 entropy per head, 9..13 policy loss per head, 14 adv mean, 15 adv std (unbiased)
+ *   n_actions [5] int32: rows with a taken action per head (optimizer.py:626,643)
+ *   workspace: DC_PPO_WORKSPACE_BYTES of scratch (zeroed by the call itself).
+ * Two launches: statistics (counts, advantage mean/std), then loss+grad.
+ */
+#define DC_PPO_WORKSPACE_BYTES 512
+int dc_ppo_loss_fwd_bwd(const float *const logits[DC_NUM_HEADS],
+                        const uint8_t *const masks[DC_NUM_HEADS],
+                        const uint8_t *const actions[DC_NUM_HEADS], const float *old_logp,
+                        const float *adv_raw, const float *ret, const float *value, int64_t N,
+                        float e_clip, float entropy_coef, float vf_coef,
+                        float *const dlogits[DC_NUM_HEADS], float *dvalue, float *out,
+                        int32_t *n_actions, void *workspace, dc_stream_t stream);
+
+/* Log-prob of the taken action per head, [N,5] dense (0 where the head took no action):
+ * the no-grad half of experiences_from_rollout (optimizer.py:387-390). */
+int dc_selected_logp(const float *const logits[DC_NUM_HEADS],
+                     const uint8_t *const masks[DC_NUM_HEADS],
+                     const uint8_t *const actions[DC_NUM_HEADS], int64_t N, float *logp_out,
+                     dc_stream_t stream);
+
+/* ---- gradient finish: count-divide, grad-norm metrics, clip, Adam ------------------------
+ * Replaces distributed.py:57 (grad /= has_grad_count), optimizer.py:674-681 (mean_gradient_norm
+ * x2, clip_grad_norm_(0.5), NaN guard, Adam.step) on ONE flat fp32 buffer holding all params.
+ *   flat_grad  [total + n_seg]  gradients, followed by n_seg has-grad counts (after the
+ *                               all-reduce: number of ranks that had a gradient, distributed.py:36-37)
+ *   seg_off    [n_seg+1] int64  parameter p covers flat elements seg_off[p] .. seg_off[p+1]-1
+ *   seg_head   [n_seg]   int32  -1 = always has a gradient; h>=0 = has one only if head h took
+ *                               an action this batch (optimizer.py:627-630: skipped heads leave
+ *                               .grad = None, so Adam and the norm mean skip those tensors)
+ *   steps      [n_seg]   int32  per-parameter Adam step counters (in/out)
+ *   loss_out   the `out` vector of dc_ppo_loss_fwd_bwd (NaN guard, optimizer.py:667,678)
+ *   metrics [4] fp32 out: 0 mean grad norm unclipped, 1 clipped, 2 total norm, 3 nan flag (1 =
+ *                               NaN seen, parameters left untouched -- the caller raises ValueError)
+ * dc_grad_flags writes the local has-grad flags (1/0) into flat_grad[total ..] before the all-reduce.
+ */
+int dc_grad_flags(float *flat_grad, int64_t total, const int32_t *seg_head, int n_seg,
+                  const int32_t *n_actions, dc_stream_t stream);
+int dc_grad_finish(float *flat_param, float *flat_grad, float *exp_avg, float *exp_avg_sq,
+                   int32_t *steps, const int64_t *seg_off, const int32_t *seg_head, int n_seg,
+                   int64_t total, double lr, double beta1, double beta2, double adam_eps,
+                   double max_norm, const float *loss_out, float *metrics, void *workspace,
+                   dc_stream_t stream);
+#define DC_FINISH_WORKSPACE_BYTES 1024
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOTACLIENT_B200_H */

@@ -1,0 +1,63 @@
+"""CPU tests of the C-ABI boundary: the library builds, loads, and exports every declared symbol."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dotaclient_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dotaclient_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "declared in include/dotaclient_b200.h but not exported: " + n
+
+
+def test_ctypes_signatures_cover_the_header():
+    from dotaclient_b200 import _lib
+    assert set(declared_symbols()) <= set(_lib.SIGNATURES)
+
+
+def test_version_and_argument_errors_without_gpu(lib):
+    assert lib.dc_version() >= 100
+    # argument validation happens before any CUDA call, so it is testable on a CPU-only box
+    rc = lib.dc_gae_scan(None, 0, None, None, 1, None, None, 0.98, 0.97, None, None, None)
+    assert rc == -1 and b"dc_gae_scan" in lib.dc_last_error()
+    rc = lib.dc_rnn_seq_fwd(7, None, None, None, None, None, 1, 1, 128, None, None)
+    assert rc == -1 and b"unknown cell" in lib.dc_last_error()
+    rc = lib.dc_rnn_seq_fwd(1, None, None, None, None, None, 1, 1, 130, None, None)
+    assert rc == -2
+    assert lib.dc_rnn_workspace_bytes(1, 128) == 4 * 128 * 128 * 4
+
+
+def test_sass_is_sm100a_only():
+    import subprocess
+    so = os.path.join(ROOT, "dotaclient_b200", "libdotaclient_b200.so")
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no file of the product package may reference it."""
+    pkg = os.path.join(ROOT, "dotaclient_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "reference_shim" not in text, f

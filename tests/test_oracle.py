@@ -1,0 +1,164 @@
+"""CPU tests: the oracle against the reference's recorded outputs (tests/golden) and, where the
+reference tree is present (build container), against the reference itself bit-for-bit."""
+import copy
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_shim
+from oracle import ref_optimizer as RO
+from oracle.ref_policy import RefPolicy, masked_softmax, sample_index
+from dotaclient_b200.synthetic import make_rollout
+
+HEADS = ("enum", "x", "y", "target_unit", "ability")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _c_gae():
+    so = os.path.join(ROOT, "oracle", "libgae_ref.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(so)
+    lib.gae_ref.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double, ctypes.c_double,
+                            ctypes.c_void_p, ctypes.c_void_p]
+
+    def run(r, v, gamma=0.98, lam=0.97):
+        n = len(r) - 1
+        a, q = np.empty(n, np.float32), np.empty(n, np.float32)
+        lib.gae_ref(r.ctypes.data, v.ctypes.data, n, gamma, lam, a.ctypes.data, q.ctypes.data)
+        return a, q
+    return run
+
+
+def test_gae_known_answer(gae_golden):
+    """SURVEY.md 4 known-answer vector + a 300-step vector recorded from the reference's advantage_returns."""
+    a, q = RO.advantage_returns(gae_golden["r"], gae_golden["v"])
+    np.testing.assert_array_equal(a, gae_golden["adv"])
+    np.testing.assert_array_equal(q, gae_golden["ret"])
+    np.testing.assert_allclose(a, [2.3829143, 1.4653, 0.5], rtol=1e-6)
+    np.testing.assert_allclose(q, [2.9404, 1.98, 1.0], rtol=1e-6)
+    a2, q2 = RO.advantage_returns(gae_golden["r2"], gae_golden["v2"])
+    np.testing.assert_array_equal(a2, gae_golden["adv2"])
+    np.testing.assert_array_equal(q2, gae_golden["ret2"])
+
+
+def test_c_gae_matches_scipy_restatement(gae_golden):
+    run = _c_gae()
+    a, q = run(gae_golden["r2"], gae_golden["v2"])
+    np.testing.assert_array_equal(a, gae_golden["adv2"])
+    np.testing.assert_array_equal(q, gae_golden["ret2"])
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 31, 32, 33, 1000):
+        r = np.append(rng.randn(n).astype(np.float32), np.float32(0))
+        v = np.append(rng.randn(n).astype(np.float32), np.float32(0))
+        a, q = run(r, v)
+        a2, q2 = RO.advantage_returns(r, v)
+        np.testing.assert_array_equal(a, a2)
+        np.testing.assert_array_equal(q, q2)
+
+
+def test_numpy_reward_sum_order():
+    """The GAE kernel reproduces numpy's pairwise add-reduce order for 10 sub-rewards (optimizer.py:397)."""
+    rng = np.random.RandomState(1)
+    x = (rng.randn(257, 10) * 3).astype(np.float32)
+    f = np.float32
+    manual = np.array([f(f(f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7]))) + r[8]) + r[9])
+                       for r in x], dtype=np.float32)
+    np.testing.assert_array_equal(np.sum(x, axis=1), manual)
+
+
+def _oracle(seq_len=16):
+    torch.manual_seed(7)
+    return RO.RefOptimizer(RefPolicy(256, "gru"), seq_len=seq_len)
+
+
+def test_oracle_reproduces_reference_golden(golden):
+    """Oracle == recorded reference outputs, bit for bit (init, prep, forward, three train epochs)."""
+    torch.set_num_threads(1)
+    opt = _oracle(int(golden["seq_len"]))
+    sd = opt.policy_base.state_dict()
+    assert list(sd.keys()) == [str(n) for n in golden["param_names"]]
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd.values()]), golden["init_param_sums"])
+    data = make_rollout(int(golden["rollout_len"]), int(golden["rollout_seed"]))
+    seqs = opt.experiences_from_rollout(copy.deepcopy(data))
+    np.testing.assert_array_equal(np.stack([s.advantages.numpy() for s in seqs]), golden["advantages"])
+    np.testing.assert_array_equal(np.stack([s.returns.numpy() for s in seqs]), golden["returns"])
+    np.testing.assert_array_equal(np.stack([s.values.numpy().reshape(-1) for s in seqs]), golden["values"])
+    np.testing.assert_array_equal(np.stack([s.hidden.numpy().reshape(-1) for s in seqs]), golden["hidden"])
+    for k in HEADS:
+        np.testing.assert_array_equal(torch.cat([s.log_probs_sel[k] for s in seqs]).numpy(), golden["old_logp_" + k])
+    (_, _, _, _, _), logits, values = opt.loss_only(seqs)
+    for k in HEADS:
+        np.testing.assert_array_equal(logits[k].detach().numpy(), golden["logits_" + k])
+    np.testing.assert_array_equal(values.detach().numpy(), golden["forward_values"])
+    for ep in range(int(golden["epochs"])):
+        l, e, g = opt.train(seqs)
+        got = [float(l[k]) for k in ("loss", "policy_loss", "entropy_loss", "value_loss")]
+        np.testing.assert_array_equal(np.array(got), golden["losses"][ep])
+        np.testing.assert_array_equal(np.array([float(e[k]) for k in HEADS]), golden["entropies"][ep])
+        np.testing.assert_array_equal(np.array([float(g["unclipped"]), float(g["clipped"])]), golden["grad_norms"][ep])
+    sd = opt.policy_base.state_dict()
+    np.testing.assert_array_equal(np.array([float(v.double().sum()) for v in sd.values()]), golden["final_param_sums"])
+    np.testing.assert_array_equal(sd["rnn.bias_hh_l0"].numpy(), golden["final_rnn_bias_hh"])
+
+
+@pytest.mark.skipif(not reference_shim.available(), reason="reference tree not present (GPU box)")
+def test_oracle_bit_identical_to_reference_live():
+    """Restatement vs the reference imported in place, ragged rollout, 2 epochs."""
+    torch.set_num_threads(1)
+    ref = reference_shim.make_reference_optimizer(seq_len=8)
+    mine = _oracle(8)
+    data = make_rollout(29, 5)
+    with torch.no_grad():
+        xr = ref.experiences_from_rollout(copy.deepcopy(data))
+    xm = mine.experiences_from_rollout(copy.deepcopy(data))
+    assert len(xr) == len(xm) == 4
+    for a, b in zip(xr, xm):
+        assert torch.equal(a.advantages, b.advantages) and torch.equal(a.returns, b.returns)
+        assert torch.equal(a.hidden, b.hidden)
+    for _ in range(2):
+        lr_, er_, gr_ = ref.train(xr)
+        lm_, em_, gm_ = mine.train(xm)
+        assert all(torch.equal(lr_[k], lm_[k]) for k in lr_)
+        assert all(torch.equal(er_[k], em_[k]) for k in er_)
+        assert torch.equal(gr_["unclipped"], gm_["unclipped"]) and torch.equal(gr_["clipped"], gm_["clipped"])
+    for (n, p), (_, q) in zip(ref.policy_base.state_dict().items(), mine.policy_base.state_dict().items()):
+        assert torch.equal(p, q), n
+
+
+def test_oracle_lstm_and_width_variants_run():
+    """The widths/cell the reference cannot express: shapes, finite losses, state_dict layout."""
+    for H, cell in ((128, "lstm"), (128, "gru"), (512, "lstm")):
+        torch.manual_seed(7)
+        opt = RO.RefOptimizer(RefPolicy(H, cell), seq_len=8)
+        G = 4 if cell == "lstm" else 3
+        sd = opt.policy_base.state_dict()
+        assert len(sd) == 34 and sd["rnn.weight_hh_l0"].shape == (G * H, H)
+        seqs = opt.experiences_from_rollout(make_rollout(20, 3))
+        l, e, g = opt.train(seqs)
+        assert np.isfinite(float(l["loss"])) and np.isfinite(float(g["unclipped"]))
+
+
+def test_masked_softmax_semantics():
+    """policy.py:169-178: normalised over the mask, masked-out entries keep finite junk, empty rows -> +inf."""
+    logits = torch.tensor([[[1.0, 2.0, 3.0], [0.5, 0.5, 0.5]]])
+    mask = torch.tensor([[[True, False, True], [False, False, False]]])
+    lp = masked_softmax(logits, mask)
+    ref = torch.log_softmax(torch.tensor([1.0, 3.0]), 0)
+    assert torch.allclose(lp[0, 0, [0, 2]], ref)
+    assert torch.isfinite(lp[0, 0, 1])
+    assert torch.isinf(lp[0, 1]).all()
+
+
+def test_sample_index_function():
+    logits = torch.tensor([0.1, 2.0, -1.0, 0.3])
+    mask = torch.tensor([True, False, True, True])
+    p = torch.softmax(logits[mask], 0).numpy()
+    edges = np.cumsum(p)
+    valid = [0, 2, 3]
+    for u in (0.0, 0.1, 0.3, 0.5, 0.9, 0.999):
+        assert sample_index(logits, mask, u) == valid[int(np.searchsorted(edges, u, side="right").clip(0, 2))]
