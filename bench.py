@@ -68,37 +68,70 @@ def measured_peak_hbm():
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
+def log(msg):
+    sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
+def usable_cores():
+    """Cores this process may actually use: affinity mask, capped by the cgroup CPU quota if there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_steps_per_sec(cfg, budget_s=20.0, threads=None):
     """The oracle port of the reference's ``DotaOptimizer.train`` (optimizer.py:581-689) on the host cores.
 
-    Bounded sample: a batch of ``b`` sequences of the config's seq_len/hidden/cell chosen so that one step takes a
-    few seconds; steps/s for the full batch is extrapolated linearly in the batch size (the work is per-token).
+    Bounded sample: ``b`` sequences of the config's seq_len/hidden/cell; ``b`` starts at 1 and doubles until one
+    step takes >= 1 s (or b reaches the config's batch), then steps are timed for ~budget_s.  steps/s for the full
+    batch is extrapolated linearly in the batch size (the work is per-token).
     """
     import torch
     from oracle import ref_optimizer as RO
     from oracle.ref_policy import RefPolicy
     from dotaclient_b200.synthetic import make_rollout
-    cores = threads or os.cpu_count() or 1
+    cores = threads or min(usable_cores(), 64)            # torch CPU stops scaling on these GEMM sizes long before 64
     torch.set_num_threads(cores)
     S, H, cell, B = cfg["seq_len"], cfg["hidden"], cfg["cell"], cfg["batch"]
-    b = max(1, min(B, max(1, 8192 // S)))                 # ~8k tokens per sample step
     torch.manual_seed(7)
     opt = RO.RefOptimizer(RefPolicy(H, cell), seq_len=S)
-    seqs = []
-    for i in range(b):
-        seqs.extend(opt.experiences_from_rollout(make_rollout(S, 7 + i)))
-    opt.train(seqs)                                        # warm-up
+    seqs = opt.experiences_from_rollout(make_rollout(S, 7))
+    b = 1
+    t_begin = time.perf_counter()
+    while True:
+        t0 = time.perf_counter()
+        opt.train(seqs)                                    # also the warm-up
+        dt = time.perf_counter() - t0
+        if dt >= 1.0 or b >= B or b >= 32 or time.perf_counter() - t_begin > budget_s / 2:
+            break
+        for i in range(b):
+            seqs.extend(opt.experiences_from_rollout(make_rollout(S, 7 + b + i)))
+        b *= 2
     t0, n = time.perf_counter(), 0
     while True:
         opt.train(seqs)
         n += 1
         el = time.perf_counter() - t0
-        if el > budget_s or n >= 20:
+        if el > budget_s / 2 or n >= 20:
             break
+    b = len(seqs)
     sample_steps_per_s = n / el
     full = sample_steps_per_s * b / B
-    sample = "oracle port of optimizer.py:581-689, batch %d x seq %d (hidden %d, %s), %d steps in %.1f s; scaled x%d/%d to batch %d" % (
-        b, S, H, cell, n, el, b, B, B)
+    sample = "oracle port of optimizer.py:581-689, batch %d x seq %d (hidden %d, %s), %d steps in %.1f s on %d threads; " \
+             "scaled x%d/%d to batch %d" % (b, S, H, cell, n, el, cores, b, B, B)
     return full, cores, sample
 
 
@@ -108,7 +141,7 @@ def run_reference_arm(args, cfg):
     if rank != 0:
         return
     steps_per_s_samples = []
-    cores, sample = os.cpu_count() or 1, ""
+    cores, sample = usable_cores(), ""
     per = max(3.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
         v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=per)
@@ -197,6 +230,7 @@ def main():
                         entropy_coef=5e-4, vf_coef=0.5, run_local=True, hidden_size=H, cell=cell)
     # synthetic experience: B rollouts of exactly S steps per rank, prepared by the product's own
     # experiences_from_rollout (old log-probs, values, GAE under the current weights), then stacked once.
+    log("optimizer built; preparing %d rollouts of %d steps" % (B, S))
     seqs = []
     with torch.no_grad():
         for i in range(B):
@@ -206,6 +240,7 @@ def main():
     batch_host = batch_dev.pin_memory()
     h2d_bytes = batch_host.nbytes()
     torch.cuda.synchronize()
+    log("experience batch ready: %.1f MB" % (h2d_bytes / 1e6))
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,17 +266,20 @@ def main():
     step_e2e = lambda: opt.train(batch_host)         # noqa: E731
     for _ in range(max(3, args.warmup)):
         step_dev()
+    log("warm-up done")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     ops.PROFILE.reset(enabled=True)
     ms_total = timed(step_dev, args.steps)
+    log("timed region (HBM-resident) done: %.2f ms/step" % (ms_total / args.steps))
     prof = ops.PROFILE.summary(args.steps)
     launches = ops.PROFILE.launches
     ops.PROFILE.reset(enabled=False)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    log("timed region (e2e) done: %.2f ms/step" % (ms_e2e / args.steps))
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -273,6 +311,7 @@ def main():
         "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
     if not args.no_cpu_baseline:
+        log("timing the CPU baseline (oracle port)")
         v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=20.0)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line))

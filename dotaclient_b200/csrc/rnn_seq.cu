@@ -25,11 +25,12 @@ extern "C" int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const f
     DC_REQUIRE(gates && w_hh && b_hh && ybuf && cbuf && workspace, DC_EINVAL, "dc_rnn_seq_fwd: null pointer");
     cudaStream_t st = dc_cu_stream(stream);
     const int G = cell == DC_CELL_GRU ? 3 : 4;
-    if (dc_rnn::resident_supported(cell, H)) return dc_rnn::launch_fwd_resident(cell, gates, w_hh, b_hh, ybuf, cbuf, B, S, H, st);
+    // both forward kernels read W_hh^T [H, G*H] so that output columns are contiguous (coalesced / float4)
     float *wT = reinterpret_cast<float *>(workspace);
     dim3 tb(32, 8), tg((H + 31) / 32, (G * H + 31) / 32);
     dc_rnn::transpose_kernel<<<tg, tb, 0, st>>>(w_hh, wT, G * H, H);
     DC_LAUNCH_OK();
+    if (dc_rnn::resident_supported(cell, H)) return dc_rnn::launch_fwd_resident(cell, gates, wT, b_hh, ybuf, cbuf, B, S, H, st);
     const int blocks = (B + dc_rnn::kBT - 1) / dc_rnn::kBT;
     const size_t smem = (size_t)dc_rnn::kBT * (G + 1) * H * sizeof(float);
     if (G == 3) {

@@ -124,7 +124,8 @@ def _torch_rnn(cell, H):
 
 
 @pytest.mark.parametrize("cell", ["gru", "lstm"])
-@pytest.mark.parametrize("B,S,H", [(3, 7, 128), (2, 40, 128), (5, 16, 256), (2, 5, 512), (9, 33, 128), (1, 1, 64)])
+@pytest.mark.parametrize("B,S,H", [(3, 7, 128), (2, 40, 128), (5, 16, 256), (2, 5, 512), (9, 33, 128), (1, 1, 64),
+                                   (301, 6, 128), (1, 3, 128)])
 def test_rnn_forward_backward_vs_torch(cell, B, S, H):
     """Recurrence kernels (+ cuBLAS i2h) against torch.nn.GRU / nn.LSTM on CPU: outputs, final state, all grads."""
     from dotaclient_b200 import ops
