@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(G *kH, 1) fwd_resident_kernel(float *__restric
                                                                  float *__restrict__ cbuf, int B, int S) {
     using SM = FwdSmem<G, BT>;
     constexpr int NT = SM::NT, GH = SM::GH, H = kH;
+    static_assert(BT * kH <= G * kH, "one gate thread per (sequence, unit) pair");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *w_s = reinterpret_cast<float4 *>(smem_raw);
     float *in_s = reinterpret_cast<float *>(smem_raw + SM::w_bytes);
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(G *kH, 1) bwd_resident_kernel(float *__restric
                                                                  float *__restrict__ dc0, int B, int S) {
     using SM = BwdSmem<G, BT>;
     constexpr int NT = SM::NT, GH = SM::GH, H = kH, NMS = SM::NMS;
+    static_assert(BT * kH <= G * kH, "one gate thread per (sequence, unit) pair");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *w_s = reinterpret_cast<float4 *>(smem_raw);
     float *in_s = reinterpret_cast<float *>(smem_raw + SM::w_bytes);
@@ -380,26 +382,27 @@ int launch_bwd_t(float *gates, const float *w, const float *ybuf, float *cbuf, c
     return DC_OK;
 }
 
-// kBT: the smallest batch tile that still fits the batch in one wave of CTAs (1 CTA / SM).
-inline int pick_bt(int B) { return (B + 1) / 2 <= dc_sm_count() ? 2 : 4; }
+// kBT: the smallest batch tile that still fits the batch in one wave of CTAs (1 CTA / SM).  The gate phase maps one
+// thread to one (sequence, unit) pair, so kBT * H must not exceed the CTA size G * H: kBT <= 3 (GRU) / 4 (LSTM).
+inline bool small_tile(int B) { return (B + 1) / 2 <= dc_sm_count(); }
 
 inline int launch_fwd_resident(int cell, float *gates, const float *wT, const float *b_hh, float *ybuf, float *cbuf, int B,
                                int S, int H, cudaStream_t st) {
     (void)H;
-    const int bt = pick_bt(B);
     if (cell == DC_CELL_GRU)
-        return bt == 2 ? launch_fwd_t<3, 2>(gates, wT, b_hh, ybuf, cbuf, B, S, st) : launch_fwd_t<3, 4>(gates, wT, b_hh, ybuf, cbuf, B, S, st);
-    return bt == 2 ? launch_fwd_t<4, 2>(gates, wT, b_hh, ybuf, cbuf, B, S, st) : launch_fwd_t<4, 4>(gates, wT, b_hh, ybuf, cbuf, B, S, st);
+        return small_tile(B) ? launch_fwd_t<3, 2>(gates, wT, b_hh, ybuf, cbuf, B, S, st)
+                             : launch_fwd_t<3, 3>(gates, wT, b_hh, ybuf, cbuf, B, S, st);
+    return small_tile(B) ? launch_fwd_t<4, 2>(gates, wT, b_hh, ybuf, cbuf, B, S, st)
+                         : launch_fwd_t<4, 4>(gates, wT, b_hh, ybuf, cbuf, B, S, st);
 }
 inline int launch_bwd_resident(int cell, float *gates, const float *w, const float *ybuf, float *cbuf, const float *dy,
                                const float *dhn, const float *dcn, float *dh0, float *dc0, int B, int S, int H, cudaStream_t st) {
     (void)H;
-    const int bt = pick_bt(B);
     if (cell == DC_CELL_GRU)
-        return bt == 2 ? launch_bwd_t<3, 2>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st)
-                       : launch_bwd_t<3, 4>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st);
-    return bt == 2 ? launch_bwd_t<4, 2>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st)
-                   : launch_bwd_t<4, 4>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st);
+        return small_tile(B) ? launch_bwd_t<3, 2>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st)
+                             : launch_bwd_t<3, 3>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st);
+    return small_tile(B) ? launch_bwd_t<4, 2>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st)
+                         : launch_bwd_t<4, 4>(gates, w, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st);
 }
 
 }  // namespace dc_rnn

@@ -162,3 +162,52 @@ def test_sample_index_function():
     valid = [0, 2, 3]
     for u in (0.0, 0.1, 0.3, 0.5, 0.9, 0.999):
         assert sample_index(logits, mask, u) == valid[int(np.searchsorted(edges, u, side="right").clip(0, 2))]
+
+
+# ------------------------------------------------------------------------------------------------ N-rank oracle
+def _reference_rank_worker(rank, world, port, out_dir):
+    """Runs the UNMODIFIED reference distributed.py + optimizer.train under gloo (prep through policy_base)."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    O, P, D = reference_shim.load()
+    opt = reference_shim.make_reference_optimizer(seq_len=8)
+    with torch.no_grad():
+        xs = opt.experiences_from_rollout(make_rollout(24, 300 + rank))
+    opt.policy = D.DistributedDataParallelSparseParamCPU(opt.policy_base)
+    opt.optimizer = torch.optim.Adam(opt.policy.parameters(), lr=5e-5)
+    recs = []
+    for _ in range(2):
+        l, e, g = opt.train(xs)
+        recs.append(([float(l[k]) for k in ("loss", "policy_loss", "entropy_loss", "value_loss")],
+                     float(g["unclipped"]), float(g["clipped"])))
+    torch.save({"recs": recs, "sd": opt.policy_base.state_dict()}, os.path.join(out_dir, "ref_rank%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not reference_shim.available(), reason="reference tree not present (GPU box)")
+def test_nrank_oracle_matches_reference_under_gloo(tmp_path):
+    """oracle/ref_distributed.py (one-process emulation) == 2 gloo processes running the reference's wrapper."""
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import ref_distributed
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_reference_rank_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    torch.set_num_threads(1)
+    opts = [_oracle(8) for _ in range(2)]
+    shards = [opts[r].experiences_from_rollout(make_rollout(24, 300 + r)) for r in range(2)]
+    mine = [ref_distributed.train_ranks(opts, shards) for _ in range(2)]
+    for r in range(2):
+        ref = torch.load(os.path.join(str(tmp_path), "ref_rank%d.pt" % r))
+        for ep in range(2):
+            l, e, g = mine[ep][r]
+            got = [float(l[k]) for k in ("loss", "policy_loss", "entropy_loss", "value_loss")]
+            np.testing.assert_array_equal(np.array(got), np.array(ref["recs"][ep][0]))
+            np.testing.assert_allclose(float(g["unclipped"]), ref["recs"][ep][1], rtol=1e-6)
+            np.testing.assert_allclose(float(g["clipped"]), ref["recs"][ep][2], rtol=1e-6)
+        for k, v in opts[r].policy_base.state_dict().items():
+            torch.testing.assert_close(v, ref["sd"][k], rtol=0, atol=1e-7, msg=lambda m: k + m)
