@@ -47,6 +47,9 @@ def parse_args():
     p.add_argument("--seq-len", type=int, default=None)
     p.add_argument("--hidden", type=int, default=None)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cuda-profiler", action="store_true",
+                   help="bracket the HBM-resident timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
+    p.add_argument("--skip-e2e", action="store_true", help="(profiling only) skip the host-buffer timed region")
     return p.parse_args()
 
 
@@ -271,14 +274,21 @@ def main():
     if rank == 0:
         sampler.start()
     ops.PROFILE.reset(enabled=True)
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     ms_total = timed(step_dev, args.steps)
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     log("timed region (HBM-resident) done: %.2f ms/step" % (ms_total / args.steps))
     prof = ops.PROFILE.summary(args.steps)
     launches = ops.PROFILE.launches
     ops.PROFILE.reset(enabled=False)
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    if args.skip_e2e:
+        ms_e2e = float("nan")
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
     log("timed region (e2e) done: %.2f ms/step" % (ms_e2e / args.steps))
     clocks = sampler.stop() if rank == 0 else None
 

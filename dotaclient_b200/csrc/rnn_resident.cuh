@@ -65,65 +65,83 @@ struct Tiling {
     static constexpr int M = NMS * 32;
 };
 
+// Weights are held as (row 2j, row 2j+1) PAIRS so that the inner product runs on the packed fp32x2 FMA of
+// sm_100 (FFMA2, __ffma2_rn): one instruction = two FMAs on 64-bit register pairs.  A plain 3-register FFMA issues
+// at half rate on this SM (register-bank limited); FFMA2 restores the full 128 FMA/clk/SM.  The (h[2j], h[2j+1])
+// operand pairs fall out of the 16-byte shared-memory loads for free; even and odd rows accumulate separately and
+// are added once at the end.
 template <int NT, int NOUT>
-__device__ __forceinline__ void load_weights(const float *__restrict__ A, float (&wr)[16][4], float4 *w_s) {
+__device__ __forceinline__ void load_weights(const float *__restrict__ A, float2 (&wr)[8][4], float4 *w_s) {
     using T = Tiling<NT, NOUT>;
     const int cg = threadIdx.x % T::NCG, ms = threadIdx.x / T::NCG;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(ms * 32 + i) * NOUT) + cg);
-        wr[i][0] = v.x; wr[i][1] = v.y; wr[i][2] = v.z; wr[i][3] = v.w;
+    for (int j = 0; j < 8; ++j) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(ms * 32 + 2 * j) * NOUT) + cg);
+        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(ms * 32 + 2 * j + 1) * NOUT) + cg);
+        wr[j][0] = make_float2(r0.x, r1.x); wr[j][1] = make_float2(r0.y, r1.y);
+        wr[j][2] = make_float2(r0.z, r1.z); wr[j][3] = make_float2(r0.w, r1.w);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-        w_s[(ms * 16 + i) * T::NCG + cg] = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(ms * 32 + 16 + i) * NOUT) + cg);
+    for (int j = 0; j < 8; ++j) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(ms * 32 + 16 + 2 * j) * NOUT) + cg);
+        const float4 r1 = __ldg(reinterpret_cast<const float4 *>(A + (size_t)(ms * 32 + 17 + 2 * j) * NOUT) + cg);
+        w_s[((ms * 8 + j) * 2 + 0) * T::NCG + cg] = make_float4(r0.x, r1.x, r0.y, r1.y);
+        w_s[((ms * 8 + j) * 2 + 1) * T::NCG + cg] = make_float4(r0.z, r1.z, r0.w, r1.w);
+    }
 }
 
 // part_s[ms][b][n] = sum over this thread's 32 rows of in_s[b][m] * A[m][n]
 template <int NT, int NOUT, int BT>
-__device__ __forceinline__ void matvec_partial(const float (&wr)[16][4], const float4 *w_s, const float *in_s, float *part_s) {
+__device__ __forceinline__ void matvec_partial(const float2 (&wr)[8][4], const float4 *w_s, const float *in_s, float *part_s) {
     using T = Tiling<NT, NOUT>;
     const int cg = threadIdx.x % T::NCG, ms = threadIdx.x / T::NCG;
-    float acc[BT][4];
+    float2 acc[BT][4];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[b][c] = make_float2(0.f, 0.f);
     const float *in0 = in_s + ms * 32;
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {           // register-resident rows
+    for (int j = 0; j < 8; j += 2) {            // register-resident rows 0..15
         float4 hv[BT];
 #pragma unroll
-        for (int b = 0; b < BT; ++b) hv[b] = *reinterpret_cast<const float4 *>(in0 + b * T::M + i);
+        for (int b = 0; b < BT; ++b) hv[b] = *reinterpret_cast<const float4 *>(in0 + b * T::M + 2 * j);
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-            const float e[4] = {hv[b].x, hv[b].y, hv[b].z, hv[b].w};
+            const float2 h0 = make_float2(hv[b].x, hv[b].y), h1 = make_float2(hv[b].z, hv[b].w);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[b][c] = fmaf(e[q], wr[i + q][c], acc[b][c]);
+            for (int c = 0; c < 4; ++c) {
+                acc[b][c] = __ffma2_rn(h0, wr[j][c], acc[b][c]);
+                acc[b][c] = __ffma2_rn(h1, wr[j + 1][c], acc[b][c]);
+            }
         }
     }
     const float4 *wp = w_s + (ms * 16) * T::NCG + cg;
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {           // shared-memory-resident rows
+    for (int j = 0; j < 8; j += 2) {            // shared-memory-resident rows 16..31
         float4 hv[BT];
 #pragma unroll
-        for (int b = 0; b < BT; ++b) hv[b] = *reinterpret_cast<const float4 *>(in0 + b * T::M + 16 + i);
+        for (int b = 0; b < BT; ++b) hv[b] = *reinterpret_cast<const float4 *>(in0 + b * T::M + 16 + 2 * j);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 w = wp[(i + q) * T::NCG];
+        for (int p = 0; p < 2; ++p) {
+            const float4 wa = wp[((j + p) * 2 + 0) * T::NCG];
+            const float4 wb = wp[((j + p) * 2 + 1) * T::NCG];
+            const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w);
+            const float2 w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
 #pragma unroll
             for (int b = 0; b < BT; ++b) {
-                const float e = q == 0 ? hv[b].x : q == 1 ? hv[b].y : q == 2 ? hv[b].z : hv[b].w;
-                acc[b][0] = fmaf(e, w.x, acc[b][0]);
-                acc[b][1] = fmaf(e, w.y, acc[b][1]);
-                acc[b][2] = fmaf(e, w.z, acc[b][2]);
-                acc[b][3] = fmaf(e, w.w, acc[b][3]);
+                const float2 h = p == 0 ? make_float2(hv[b].x, hv[b].y) : make_float2(hv[b].z, hv[b].w);
+                acc[b][0] = __ffma2_rn(h, w0, acc[b][0]);
+                acc[b][1] = __ffma2_rn(h, w1, acc[b][1]);
+                acc[b][2] = __ffma2_rn(h, w2, acc[b][2]);
+                acc[b][3] = __ffma2_rn(h, w3, acc[b][3]);
             }
         }
     }
 #pragma unroll
     for (int b = 0; b < BT; ++b)
-        *reinterpret_cast<float4 *>(part_s + ((ms * BT + b) * NOUT) + cg * 4) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+        *reinterpret_cast<float4 *>(part_s + ((ms * BT + b) * NOUT) + cg * 4) =
+            make_float4(acc[b][0].x + acc[b][0].y, acc[b][1].x + acc[b][1].y, acc[b][2].x + acc[b][2].y, acc[b][3].x + acc[b][3].y);
 }
 
 template <int G, int BT>
@@ -157,7 +175,7 @@ __global__ void __launch_bounds__(G *kH, 1) fwd_resident_kernel(float *__restric
     const int nb = min(BT, B - b0);
     const uint32_t tile_bytes = (uint32_t)nb * GH * 4;
 
-    float wr[16][4];
+    float2 wr[8][4];
     load_weights<NT, GH>(wT, wr, w_s);
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
@@ -264,7 +282,7 @@ __global__ void __launch_bounds__(G *kH, 1) bwd_resident_kernel(float *__restric
     const int nb = min(BT, B - b0);
     const uint32_t gate_bytes = (uint32_t)nb * GH * 4, row_bytes = (uint32_t)nb * H * 4;
 
-    float wr[16][4];
+    float2 wr[8][4];
     load_weights<NT, H>(w, wr, w_s);
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
