@@ -1,0 +1,255 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores:  C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU optional)
+//
+// Replaces the library SGEMM behind the dense layers of the hot path whose shapes are real contractions
+// -- first of all the input-to-hidden GEMM of the recurrent layer (x W_ih^T + b_ih inside nn.GRU / nn.LSTM,
+// policy.py:66,141; the one place north_star puts tensor cores) -- while keeping fp32-level accuracy, so
+// that the parity tolerances against the fp32 reference hold:
+//
+//   3xTF32 split.  a = a_hi + a_lo with a_hi = rna_tf32(a), a_lo = a - a_hi (exact in fp32);
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, three tcgen05.mma.kind::tf32 per k-step into one fp32
+//   TMEM accumulator.  The dropped a_lo*b_lo term and the truncation of the lo parts are O(2^-22).
+//
+// Structure (one CTA per SM, persistent over 128x128 output tiles, 9 warps):
+//   warps 0-3  PRODUCERS: coalesced 16-byte global loads of a [128 x 32] fp32 chunk of A and of B, hi/lo split
+//              on the CUDA cores, stores into the canonical K-major SWIZZLE_128B shared-memory layout
+//              (4 tiles of 16 KB per stage: A_hi, A_lo, B_hi, B_lo), fence.proxy.async, mbarrier arrive.
+//              (TMA cannot do this step: the split is arithmetic, so the data passes through registers anyway.)
+//   warp  4    MMA ISSUER: one elected lane issues 12 tcgen05.mma (4 k-steps x 3 products) per stage from
+//              shared-memory descriptors, tcgen05.commit releases the stage / publishes the accumulator.
+//   warps 5-8  EPILOGUE: tcgen05.ld 32x32b (one TMEM lane = one output row per thread), + bias, ReLU, 16-byte
+//              global stores.  Two TMEM accumulator buffers (2 x 128 columns) overlap the epilogue of tile i
+//              with the main loop of tile i+1.
+// Tensor-pipe work: 2*M*N*K*3 flops; HBM: 4*(M*K + N*K + M*N) bytes.  For the K=128 GEMMs of this model the
+// kernel is HBM-bound even with the 3x flops.
+#include "dc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;           // BK floats = 128 bytes = one swizzle-128B row
+constexpr int kStages = 3;
+constexpr int kTileBytes = BM * BK * 4;              // 16 KB
+constexpr int kStageBytes = 4 * kTileBytes;          // A_hi, A_lo, B_hi, B_lo
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 9 * 32;
+constexpr int kAccCols = 128, kTmemCols = 256;       // two accumulator buffers
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {   // arrives on `bar` when all prior MMAs of this thread retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (8 rows * 128 B = 1024)
+// | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24.
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// Loads rows [row0, row0+128) x cols [k0, k0+32) of a row-major fp32 matrix (ld = leading dim), splits into
+// hi/lo and stores both into K-major swizzle-128B tiles.  Rows >= rows_total are zero-filled.
+__device__ __forceinline__ void produce_tile(const float *__restrict__ src, int ld, int row0, int rows_total, int k0,
+                                             unsigned char *dst_hi, unsigned char *dst_lo, int t) {
+    const int c = t & 7, r0 = t >> 3;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 16 * i;
+        v[i] = (row0 + r < rows_total) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)(row0 + r) * ld + k0) + c)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 16 * i;
+        const int off = r * 128 + ((c ^ (r & 7)) << 4);
+        float4 hi, lo;
+        hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
+        lo.x = v[i].x - hi.x; lo.y = v[i].y - hi.y; lo.z = v[i].z - hi.z; lo.w = v[i].w - hi.w;
+        *reinterpret_cast<float4 *>(dst_hi + off) = hi;
+        *reinterpret_cast<float4 *>(dst_lo + off) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *__restrict__ A, int lda,
+                                                                  const float *__restrict__ B, int ldb,
+                                                                  const float *__restrict__ bias, float *__restrict__ C,
+                                                                  int ldc, int M, int N, int K, int relu) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages, *acc_empty = bars + 2 * kStages + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
+    const int tiles_total = m_blocks * n_blocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {   // TMEM allocation: one full warp; the address lands in shared memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== PRODUCERS =====
+        const int t = threadIdx.x;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+            const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+            for (int kc = 0; kc < k_chunks; ++kc) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                unsigned char *st = tiles + (size_t)stage * kStageBytes;
+                produce_tile(A, lda, m0, M, kc * BK, st, st + kTileBytes, t);
+                produce_tile(B, ldb, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+                mbar_arrive(&full[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 4) {
+        // ===== MMA ISSUER =====
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);                    // epilogue drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + a * kAccCols;
+            for (int kc = 0; kc < k_chunks; ++kc) {
+                mbar_wait(&full[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t base = smem_u32(tiles + (size_t)stage * kStageBytes);
+                    const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + kTileBytes);
+                    const uint64_t b_hi = make_desc(base + 2 * kTileBytes), b_lo = make_desc(base + 3 * kTileBytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {                      // UMMA_K = 8 tf32 = 32 bytes = 2 x 16 B
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t first = (kc | ks) != 0;
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, kIdesc, first);   // small terms first
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, kIdesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);                                 // stage reusable once these MMAs retire
+                    if (kc == k_chunks - 1) umma_commit(&acc_full[a]);          // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== EPILOGUE (warps 5..8; TMEM lane quadrant = warp % 4) =====
+        const int q = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++it) {
+            const int a = it & 1;
+            const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+            mbar_wait(&acc_full[a], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            float *crow = C + (size_t)row * ldc + n0;
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kAccCols + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
+                        o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
+                        if (bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + cb + j));
+                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        }
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4 *>(crow + cb + j) = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[a]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+}  // namespace
+
+extern "C" int dc_gemm_tf32x3_supported(int64_t M, int N, int K) { return M > 0 && N > 0 && K > 0 && N % BN == 0 && K % BK == 0; }
+
+extern "C" int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
+                              int64_t M, int N, int K, int relu, dc_stream_t stream) {
+    DC_REQUIRE(A && B && C, DC_EINVAL, "dc_gemm_tf32x3: null pointer");
+    DC_REQUIRE(dc_gemm_tf32x3_supported(M, N, K) && M < (1ll << 31) - BM, DC_EUNSUPPORTED,
+               "dc_gemm_tf32x3: need N %% 128 == 0 and K %% 32 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
+    DC_REQUIRE(lda >= K && ldb >= K && ldc >= N && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, DC_EINVAL,
+               "dc_gemm_tf32x3: leading dimensions must be >= extent and multiples of 4 floats");
+    DC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
+               DC_EINVAL, "dc_gemm_tf32x3: pointers must be 16-byte aligned");
+    static bool attr_set = false;
+    if (!attr_set) {
+        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
+    const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
+    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, lda, B, ldb, bias, C, ldc, (int)M, N, K, relu);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}

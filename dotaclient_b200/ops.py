@@ -307,3 +307,30 @@ def grad_finish(flat_param, flat_grad, exp_avg, exp_avg_sq, steps, seg_off, seg_
                                       seg_head.numel(), total, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                       float(max_norm), _lib.ptr(loss_out), metrics.data_ptr(), workspace.data_ptr(),
                                       _lib.stream_ptr()), "dc_grad_finish")
+
+
+# --------------------------------------------------------------------------------------------- tensor-core GEMM
+def gemm_tf32x3_supported(M, N, K):
+    return bool(_lib.load().dc_gemm_tf32x3_supported(int(M), int(N), int(K)))
+
+
+def gemm_tf32x3(a, b, bias=None, relu=False, out=None):
+    """``out[M,N] = a[M,K] @ b[N,K]^T (+ bias) (ReLU)`` on tcgen05 tensor cores with the 3xTF32 split
+    (fp32-level accuracy).  ``a``/``b``/``out`` are 2-D fp32 CUDA tensors whose rows are contiguous (row stride
+    may exceed the width: column-slice views are fine)."""
+    _need_cuda(a, b, bias)
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1]
+    if a.stride(1) != 1:
+        a = a.contiguous()
+    if b.stride(1) != 1:
+        b = b.contiguous()
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    lib = _lib.load()
+    with PROFILE.span("gemm_tf32x3", 1):
+        _lib.check(lib.dc_gemm_tf32x3(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _lib.ptr(bias), out.data_ptr(),
+                                      out.stride(0), M, N, K, 1 if relu else 0, _lib.stream_ptr()), "dc_gemm_tf32x3")
+    return out

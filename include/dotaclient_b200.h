@@ -85,6 +85,17 @@ int dc_rnn_seq_bwd(int cell, float *gates, const float *w_hh, const float *ybuf,
                    const float *dy, const float *dhn, const float *dcn, float *dh0, float *dc0,
                    int B, int S, int H, void *workspace, dc_stream_t stream);
 
+/* ---- fp32-accurate tensor-core GEMM (tcgen05, 3xTF32) ---------------------------------------
+ * C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (ReLU if relu != 0); row-major fp32 with leading dimensions lda/ldb/ldc.
+ * Replaces the library SGEMM of the input-to-hidden projection inside nn.GRU / nn.LSTM (policy.py:66,141:
+ * gates = x W_ih^T + b_ih) and of the other 128-aligned dense layers (policy.py:101-126,138).  Each product is
+ * evaluated as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with tf32 hi/lo splits (fp32-level accuracy, ~1e-6 relative).
+ * Requirements: N % 128 == 0, K % 32 == 0, 16-byte aligned pointers, ld* % 4 == 0 (dc_gemm_tf32x3_supported).
+ */
+int dc_gemm_tf32x3_supported(int64_t M, int N, int K);
+int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
+                   int64_t M, int N, int K, int relu, dc_stream_t stream);
+
 /* ---- fused PPO loss + gradient ----------------------------------------------------------
  * Replaces optimizer.py:587-589 (advantage normalisation) and :621-665 (masked log-softmax x5,
  * ratio, clipped surrogate, entropy, value loss) AND their autograd backward, for N tokens.

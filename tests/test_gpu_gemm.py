@@ -1,0 +1,54 @@
+"""GPU test of the tcgen05 3xTF32 GEMM (dc_gemm_tf32x3) against a float64 reference.
+
+Tolerance: the 3xTF32 split keeps fp32-level accuracy -- max |err| <= 4e-6 * sqrt(K) * rms(a) * rms(b)-scaled bound below,
+i.e. the same order as an fp32 SIMT GEMM and ~1000x tighter than single-pass TF32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1000, 128, 128), (129, 384, 256), (4096, 512, 128), (300, 128, 896),
+                                   (1, 128, 128), (20000, 128, 128), (777, 2048, 512)])
+@pytest.mark.parametrize("bias,relu", [(False, False), (True, False), (True, True)])
+def test_gemm_tf32x3_matches_fp64(M, N, K, bias, relu):
+    from dotaclient_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g) * 0.3
+    bv = torch.randn(N, generator=g) if bias else None
+    ref = a.double() @ b.double().t()
+    if bias:
+        ref = ref + bv.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    d = torch.device("cuda", 0)
+    out = ops.gemm_tf32x3(a.to(d), b.to(d), None if bv is None else bv.to(d), relu=relu).cpu().double()
+    err = (out - ref).abs().max().item()
+    scale = (a.double().abs() @ b.double().abs().t()).max().item()      # sum |a||b| bounds the rounding error
+    assert err <= 3e-6 * scale, (err, scale)
+    # and it is far more accurate than single-pass TF32 would be (2^-11 per operand)
+    fp32 = (a.to(d) @ b.to(d).t()).cpu().double()
+    if bias:
+        fp32 = fp32 + bv.double()
+    if relu:
+        fp32 = fp32.clamp_min(0)
+    err32 = (fp32 - ref).abs().max().item()
+    assert err <= 8 * err32 + 1e-7 * scale, (err, err32)
+
+
+def test_gemm_tf32x3_strided_views_and_unsupported_shapes():
+    from dotaclient_b200 import ops
+    d = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(1)
+    big = torch.randn(500, 512, generator=g).to(d)
+    a = big[:, 128:384]                                   # row stride 512, width 256
+    b = torch.randn(128, 256, generator=g).to(d)
+    out_big = torch.zeros(500, 256, device=d)
+    ops.gemm_tf32x3(a, b, out=out_big[:, 128:])
+    ref = (a.double() @ b.double().t())
+    assert (out_big[:, 128:].double() - ref).abs().max().item() < 1e-4
+    assert float(out_big[:, :128].abs().sum()) == 0.0
+    assert not ops.gemm_tf32x3_supported(100, 100, 128) and not ops.gemm_tf32x3_supported(100, 128, 12)
+    with pytest.raises(RuntimeError):
+        ops.gemm_tf32x3(torch.randn(10, 12, device=d), torch.randn(128, 12, device=d))

@@ -1,0 +1,49 @@
+"""Micro-benchmark of dc_gemm_tf32x3 against cuBLAS fp32 / TF32 on the model's GEMM shapes (CUDA events)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from dotaclient_b200 import ops  # noqa: E402
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def main():
+    d = torch.device("cuda", 0)
+    shapes = [("unit-embedding (16 units)", 131072 * 16, 128, 128), ("i2h lstm H128", 131072, 512, 128),
+              ("pre_rnn", 131072, 128, 896), ("i2h lstm H512 (c4)", 524288 // 4, 2048, 512)]
+    for name, M, N, K in shapes:
+        a = torch.randn(M, K, device=d)
+        b = torch.randn(N, K, device=d) * 0.1
+        bias = torch.randn(N, device=d)
+        out = torch.empty(M, N, device=d)
+        ref = torch.addmm(bias, a, b.t())
+        got = ops.gemm_tf32x3(a, b, bias, out=out)
+        err = (got - ref).abs().max().item()
+        t_ours = timeit(lambda: ops.gemm_tf32x3(a, b, bias, out=out))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        t_fp32 = timeit(lambda: torch.addmm(bias, a, b.t(), out=out))
+        torch.backends.cuda.matmul.allow_tf32 = True
+        t_tf32 = timeit(lambda: torch.addmm(bias, a, b.t(), out=out))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        flops = 2.0 * M * N * K
+        bytes_ = 4.0 * (M * K + N * K + M * N)
+        print("%-28s M=%8d N=%4d K=%4d | ours %.3f ms (%.1f TF/s eff, %.0f GB/s) | cublas fp32 %.3f ms | cublas tf32 %.3f ms | max|diff vs fp32| %.2e"
+              % (name, M, N, K, t_ours, flops / t_ours / 1e9, bytes_ / t_ours / 1e6, t_fp32, t_tf32, err))
+
+
+if __name__ == "__main__":
+    main()
