@@ -305,8 +305,16 @@ def main():
     rnn_ms = prof.get("rnn_fwd", 0.0) + prof.get("rnn_bwd", 0.0)        # average per step, CUDA events on the launch stream
     rnn_bytes = 12.0 * tokens * (G + 1) * H                             # fwd 4N(G+1)H + bwd 8N(G+1)H
     achieved = rnn_bytes / (rnn_ms * 1e-3) / 1e9 if rnn_ms > 0 else 0.0
+    traffic = None                                                      # measured DRAM bytes (ncu --set full), if captured for this shape
+    try:
+        with open(os.path.join(ROOT, "profiles", "recurrence_traffic.json")) as f:
+            rec = json.load(f).get("%s_%s" % (args.config, cell))
+        if rec and (B, S, H) == (CONFIGS[args.config]["batch"], CONFIGS[args.config]["seq_len"], CONFIGS[args.config]["hidden"]):
+            traffic = rec["fwd_bytes"] + rec["bwd_bytes"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "algorithmic_bytes_per_step": rnn_bytes, "kernel_ms_per_step": rnn_ms,
                 "share_of_step": rnn_ms / ms_per_step, "peak_source": peak_src,
                 "dependency_floor_note": "2*S=%d strictly sequential recurrence steps per optimizer step" % (2 * S),
