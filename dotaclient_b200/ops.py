@@ -9,6 +9,9 @@ import torch
 
 from . import _lib
 
+# dense layers whose shape allows it run on the tcgen05 3xTF32 GEMM (fp32-level accuracy); "0" = library SGEMM only
+_TC_ENABLED = os.environ.get("DOTACLIENT_B200_TC_GEMM", "1") == "1"
+
 CELL_ID = {"gru": 0, "lstm": 1}
 HEAD_KEYS = ("enum", "x", "y", "target_unit", "ability")     # policy.py:46
 HEAD_SIZES = (4, 9, 9, 40, 3)
@@ -142,12 +145,15 @@ def _rnn_forward_impl(x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
     N = S * B
     x2 = _f32c(x.detach()).view(N, Hin)
     w_ih, w_hh, b_ih, b_hh = _f32c(w_ih.detach()), _f32c(w_hh.detach()), _f32c(b_ih.detach()), _f32c(b_hh.detach())
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = _i2h_matmul_context()
-    try:
-        gates = torch.addmm(b_ih, x2, w_ih.t())          # [N, G*H] = x W_ih^T + b_ih
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+    if _TC_ENABLED and gemm_tf32x3_supported(N, w_ih.shape[0], Hin):
+        gates = gemm_tf32x3(x2, w_ih, b_ih)              # [N, G*H] = x W_ih^T + b_ih on tcgen05 (3xTF32)
+    else:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = _i2h_matmul_context()
+        try:
+            gates = torch.addmm(b_ih, x2, w_ih.t())
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
     ybuf = torch.empty((S + 1, B, H), dtype=torch.float32, device=x.device)
     cbuf = torch.empty((S + 1, B, H), dtype=torch.float32, device=x.device)
     ybuf[0].copy_(h0.detach().reshape(B, H))
@@ -220,7 +226,12 @@ class RnnSequence(torch.autograd.Function):
         prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
         try:
-            dx = torch.mm(dgi, w_ih).view(S, B, Hin) if ctx.needs_input_grad[0] else None
+            if not ctx.needs_input_grad[0]:
+                dx = None
+            elif _TC_ENABLED and gemm_tf32x3_supported(N, Hin, G * H):
+                dx = gemm_tf32x3(dgi, w_ih.t().contiguous()).view(S, B, Hin)     # dx = dgi W_ih on tcgen05
+            else:
+                dx = torch.mm(dgi, w_ih).view(S, B, Hin)
             dw_ih = torch.mm(dgi.t(), x2)
             db_ih = dgi.sum(0)
             if cell == "lstm":
@@ -334,3 +345,53 @@ def gemm_tf32x3(a, b, bias=None, relu=False, out=None):
         _lib.check(lib.dc_gemm_tf32x3(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _lib.ptr(bias), out.data_ptr(),
                                       out.stride(0), M, N, K, 1 if relu else 0, _lib.stream_ptr()), "dc_gemm_tf32x3")
     return out
+
+
+def _tc_ok(M, N, K):
+    return _TC_ENABLED and gemm_tf32x3_supported(M, N, K)
+
+
+class LinearTC(torch.autograd.Function):
+    """``y = x W^T + b`` (optionally ReLU) with forward and data-gradient on the tcgen05 3xTF32 GEMM.
+
+    The weight gradient ``dW = dy^T x`` contracts over the token dimension (both operands MN-major) and stays on the
+    library SGEMM for now; ``db`` is a column sum.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        shp = x.shape
+        x2 = _f32c(x.detach()).reshape(-1, shp[-1])
+        w = _f32c(weight.detach())
+        y = gemm_tf32x3(x2, w, None if bias is None else _f32c(bias.detach()), relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x2, w, y if relu else None)
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = _f32c(dy).reshape(-1, N)
+        if ctx.relu:
+            dy2 = torch.ops.aten.threshold_backward(dy2, y, 0.0)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if _tc_ok(dy2.shape[0], K, N):
+                dx = gemm_tf32x3(dy2, w.t().contiguous())
+            else:
+                dx = dy2 @ w
+            dx = dx.view(*dy.shape[:-1], K)
+        dw = torch.mm(dy2.t(), x2) if ctx.needs_input_grad[1] else None
+        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+def linear(x, weight, bias=None, relu=False):
+    """Dense layer: tensor-core path when the shape allows (N % 128 == 0, K % 32 == 0), library SGEMM otherwise."""
+    M = x.numel() // x.shape[-1]
+    if x.is_cuda and _tc_ok(M, weight.shape[0], weight.shape[1]):
+        return LinearTC.apply(x, weight, bias, relu)
+    y = torch.nn.functional.linear(x, weight, bias)
+    return torch.relu(y) if relu else y

@@ -120,13 +120,14 @@ class Policy(nn.Module):
         emb, emb_max = {}, {}
         for (suffix, _, _), units in zip(UNIT_GROUPS, groups):
             basic = F.relu(self.affine_unit_basic_stats(units))
-            emb[suffix] = getattr(self, "affine_unit_" + suffix)(basic)
+            layer = getattr(self, "affine_unit_" + suffix)
+            emb[suffix] = ops.linear(basic, layer.weight, layer.bias)          # tcgen05 3xTF32 GEMM
             emb_max[suffix] = emb[suffix].max(dim=-2)[0]
         # policy.py:127 takes the enemy-tower max from the enemy-NONHERO embedding; parity requires it.
         emb_max["eth"] = emb_max["enh"]
         unit_embedding = torch.cat([emb[s] for s, _, _ in UNIT_GROUPS], dim=-2)
         x = torch.cat([F.relu(self.affine_env(env))] + [emb_max[s] for s, _, _ in UNIT_GROUPS], dim=-1)
-        return F.relu(self.affine_pre_rnn(x)), unit_embedding
+        return ops.linear(x, self.affine_pre_rnn.weight, self.affine_pre_rnn.bias, relu=True), unit_embedding
 
     def _recur(self, x_tm, hidden):
         """x_tm ``[S, B, H]`` time-major -> y_tm ``[S, B, H]``, new hidden in the reference's ``[1, B, H]`` form."""
@@ -141,7 +142,7 @@ class Policy(nn.Module):
 
     def _heads(self, y, unit_embedding):
         """Action heads + value (``policy.py:144-155``).  Creation order as the reference's."""
-        attention = self.affine_unit_attention(y).unsqueeze(-2)
+        attention = ops.linear(y, self.affine_unit_attention.weight, self.affine_unit_attention.bias).unsqueeze(-2)
         move_x = self.affine_move_x(y)
         move_y = self.affine_move_y(y)
         head_enum = self.affine_head_enum(y)
