@@ -9,14 +9,15 @@
 //   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, three tcgen05.mma.kind::tf32 per k-step into one fp32
 //   TMEM accumulator.  The dropped a_lo*b_lo term and the truncation of the lo parts are O(2^-22).
 //
-// Structure (one CTA per SM, persistent over 128x128 output tiles, 9 warps):
-//   warps 0-3  PRODUCERS: coalesced 16-byte global loads of a [128 x 32] fp32 chunk of A and of B, hi/lo split
+// Structure (one CTA per SM, persistent over 128x128 output tiles, 13 warps):
+//   warps 0-7  PRODUCERS (two groups of 4 warps taking alternate k-chunks, so that the global-load latency of one
+//              chunk overlaps the split arithmetic of the other): coalesced 16-byte global loads of a [128 x 32] fp32 chunk of A and of B, hi/lo split
 //              on the CUDA cores, stores into the canonical K-major SWIZZLE_128B shared-memory layout
 //              (4 tiles of 16 KB per stage: A_hi, A_lo, B_hi, B_lo), fence.proxy.async, mbarrier arrive.
 //              (TMA cannot do this step: the split is arithmetic, so the data passes through registers anyway.)
-//   warp  4    MMA ISSUER: one elected lane issues 12 tcgen05.mma (4 k-steps x 3 products) per stage from
+//   warp  8    MMA ISSUER: one elected lane issues 12 tcgen05.mma (4 k-steps x 3 products) per stage from
 //              shared-memory descriptors, tcgen05.commit releases the stage / publishes the accumulator.
-//   warps 5-8  EPILOGUE: tcgen05.ld 32x32b (one TMEM lane = one output row per thread), + bias, ReLU, 16-byte
+//   warps 9-12 EPILOGUE: tcgen05.ld 32x32b (one TMEM lane = one output row per thread), + bias, ReLU, 16-byte
 //              global stores.  Two TMEM accumulator buffers (2 x 128 columns) overlap the epilogue of tile i
 //              with the main loop of tile i+1.
 // Tensor-pipe work: 2*M*N*K*3 flops; HBM: 4*(M*K + N*K + M*N) bytes.  For the K=128 GEMMs of this model the
@@ -30,7 +31,9 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = BM * BK * 4;              // 16 KB
 constexpr int kStageBytes = 4 * kTileBytes;          // A_hi, A_lo, B_hi, B_lo
 constexpr int kProducerThreads = 128;
-constexpr int kThreads = 9 * 32;
+constexpr int kProducerGroups = 2;
+constexpr int kMmaWarp = 4 * kProducerGroups;
+constexpr int kThreads = (kMmaWarp + 1 + 4) * 32;
 constexpr int kAccCols = 128, kTmemCols = 256;       // two accumulator buffers
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
 
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {   // TMEM allocation: one full warp; the address lands in shared memory
+    if (warp == kMmaWarp) {   // TMEM allocation: one full warp; the address lands in shared memory
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -128,24 +131,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // ===== PRODUCERS =====
-        const int t = threadIdx.x;
-        int stage = 0;
-        uint32_t phase = 0;
+    if (warp < kMmaWarp) {
+        // ===== PRODUCERS =====  group g takes the k-chunks whose running index is == g (mod kProducerGroups)
+        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
+        uint32_t chunk = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
             const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
-            for (int kc = 0; kc < k_chunks; ++kc) {
+            for (int kc = 0; kc < k_chunks; ++kc, ++chunk) {
+                if ((int)(chunk % kProducerGroups) != g) continue;
+                const int stage = chunk % kStages;
+                const uint32_t phase = (chunk / kStages) & 1;
                 mbar_wait(&empty[stage], phase ^ 1);
                 unsigned char *st = tiles + (size_t)stage * kStageBytes;
                 produce_tile(A, lda, m0, M, kc * BK, st, st + kTileBytes, t);
                 produce_tile(B, ldb, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
                 mbar_arrive(&full[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == kMmaWarp) {
         // ===== MMA ISSUER =====
         int stage = 0;
         uint32_t phase = 0;
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
             }
         }
     } else {
-        // ===== EPILOGUE (warps 5..8; TMEM lane quadrant = warp % 4) =====
+        // ===== EPILOGUE (4 warps; TMEM lane quadrant = warp % 4) =====
         const int q = warp & 3;
         int it = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++it) {
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }

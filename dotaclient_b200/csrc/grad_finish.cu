@@ -34,14 +34,15 @@ __global__ void grad_flags_kernel(float *flat_grad, int64_t total, const int32_t
     flat_grad[total + p] = (h < 0 || n_actions[h] > 0) ? 1.0f : 0.0f;
 }
 
-__global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(float *__restrict__ g, const int64_t *__restrict__ seg_off,
-                                                              int n_seg, int64_t total, FinishWs *ws) {
+__global__ void __launch_bounds__(kThreads) grad_sumsq_kernel(float *__restrict__ g, const int64_t *__restrict__ seg_lo,
+                                                              const int64_t *__restrict__ seg_hi, int n_seg, int64_t total,
+                                                              FinishWs *ws) {
     __shared__ double s_red[kThreads / 32];
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int p = 0; p < n_seg; ++p) {
         const float count = g[total + p];
         if (!(count > 0.f)) continue;                    // nobody has a gradient: skip (distributed.py:40-42)
-        const int64_t lo = seg_off[p], hi = seg_off[p + 1];
+        const int64_t lo = seg_lo[p], hi = seg_hi[p];
         double acc = 0.0;
         for (int64_t i = lo + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < hi; i += stride) {
             float v = g[i];
@@ -83,7 +84,8 @@ __device__ __forceinline__ void finish_scalars(const float *g_tail, int n_seg, c
 __global__ void __launch_bounds__(kThreads) adam_kernel(float *__restrict__ param, float *__restrict__ g,
                                                         float *__restrict__ m, float *__restrict__ v,
                                                         const int32_t *__restrict__ steps,
-                                                        const int64_t *__restrict__ seg_off, int n_seg, int64_t total,
+                                                        const int64_t *__restrict__ seg_lo,
+                                                        const int64_t *__restrict__ seg_hi, int n_seg, int64_t total,
                                                         double lr, double beta1_d, double beta2_d, double eps_d,
                                                         float max_norm, const float *__restrict__ loss_out,
                                                         FinishWs *ws) {
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float *__restrict__ para
         const double bc1 = 1.0 - pow(beta1_d, (double)step);
         const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, (double)step));
         const float step_size = (float)(lr / bc1);
-        const int64_t lo = seg_off[p], hi = seg_off[p + 1];
+        const int64_t lo = seg_lo[p], hi = seg_hi[p];
         for (int64_t i = lo + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < hi; i += stride) {
             const float gi = g[i] * coef;
             g[i] = gi;                                   // clipped gradient stays visible in .grad
@@ -147,11 +149,12 @@ extern "C" int dc_grad_flags(float *flat_grad, int64_t total, const int32_t *seg
 }
 
 extern "C" int dc_grad_finish(float *flat_param, float *flat_grad, float *exp_avg, float *exp_avg_sq, int32_t *steps,
-                              const int64_t *seg_off, const int32_t *seg_head, int n_seg, int64_t total, double lr,
+                              const int64_t *seg_lo, const int64_t *seg_hi, const int32_t *seg_head, int n_seg, int64_t total,
+                              double lr,
                               double beta1, double beta2, double adam_eps, double max_norm, const float *loss_out,
                               float *metrics, void *workspace, dc_stream_t stream) {
     (void)seg_head;
-    DC_REQUIRE(flat_param && flat_grad && exp_avg && exp_avg_sq && steps && seg_off && metrics && workspace,
+    DC_REQUIRE(flat_param && flat_grad && exp_avg && exp_avg_sq && steps && seg_lo && seg_hi && metrics && workspace,
                DC_EINVAL, "dc_grad_finish: null pointer");
     DC_REQUIRE(n_seg > 0 && n_seg <= kMaxSeg && total > 0, DC_EINVAL, "dc_grad_finish: n_seg=%d total=%lld", n_seg,
                (long long)total);
@@ -159,9 +162,9 @@ extern "C" int dc_grad_finish(float *flat_param, float *flat_grad, float *exp_av
     FinishWs *ws = reinterpret_cast<FinishWs *>(workspace);
     DC_CUDA(cudaMemsetAsync(ws, 0, sizeof(FinishWs), st));
     const int blocks = 2 * dc_sm_count();
-    grad_sumsq_kernel<<<blocks, kThreads, 0, st>>>(flat_grad, seg_off, n_seg, total, ws);
+    grad_sumsq_kernel<<<blocks, kThreads, 0, st>>>(flat_grad, seg_lo, seg_hi, n_seg, total, ws);
     DC_LAUNCH_OK();
-    adam_kernel<<<blocks, kThreads, 0, st>>>(flat_param, flat_grad, exp_avg, exp_avg_sq, steps, seg_off, n_seg, total,
+    adam_kernel<<<blocks, kThreads, 0, st>>>(flat_param, flat_grad, exp_avg, exp_avg_sq, steps, seg_lo, seg_hi, n_seg, total,
                                              lr, beta1, beta2, adam_eps, (float)max_norm, loss_out, ws);
     DC_LAUNCH_OK();
     finish_tail_kernel<<<1, kMaxSeg, 0, st>>>(steps, flat_grad + total, n_seg, ws, metrics);

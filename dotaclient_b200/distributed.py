@@ -97,5 +97,5 @@ class DistributedDataParallelSparseParamCPU(Module):
         if divide:
             counts = flat.flags.clamp(min=1.0)
             lengths = torch.tensor([hi - lo for lo, hi in zip(flat.offsets[:-1], flat.offsets[1:])],
-                                   device=flat.grad.device)
+                                   device=flat.grad.device)      # padded extents: the padding holds zeros
             flat.grad.div_(torch.repeat_interleave(counts, lengths))

@@ -28,6 +28,7 @@ def head_dependency(param_name):
 
 class FlatParameterSpace:
     """Re-homes ``module``'s parameters (in ``named_parameters()`` order == the reference's all-reduce order)."""
+    ALIGN = 64      # floats
 
     def __init__(self, module, device=None):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
@@ -37,22 +38,29 @@ class FlatParameterSpace:
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
         sizes = [p.numel() for p in self.params]
-        offs = [0]
+        # every tensor starts on a 256-byte boundary (16-byte alignment is required by the tensor-core GEMM and by
+        # vectorised loads); the padding elements stay zero and are never touched by the finish kernels.
+        starts, cursor = [], 0
         for s in sizes:
-            offs.append(offs[-1] + s)
-        self.total = offs[-1]
+            starts.append(cursor)
+            cursor = (cursor + s + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.total = cursor
         self.n_seg = len(sizes)
-        self.offsets = offs
-        self.param = torch.empty(self.total, dtype=torch.float32, device=device)
+        self.starts = starts
+        self.ends = [a + s for a, s in zip(starts, sizes)]
+        offs = starts + [cursor]                       # kept for compatibility: offs[i] = start of tensor i
+        self.param = torch.zeros(self.total, dtype=torch.float32, device=device)
         # gradient buffer carries n_seg extra slots: per-parameter has-grad flags / counts (distributed.py:36-37)
         self.grad_full = torch.zeros(self.total + self.n_seg, dtype=torch.float32, device=device)
         self.grad = self.grad_full[:self.total]
         self.flags = self.grad_full[self.total:]
-        for p, lo, hi in zip(self.params, offs[:-1], offs[1:]):
+        for p, lo, hi in zip(self.params, self.starts, self.ends):
             self.param[lo:hi].copy_(p.data.reshape(-1))
             p.data = self.param[lo:hi].view(p.shape)
             p.grad = self.grad[lo:hi].view(p.shape)
-        self.seg_off = torch.tensor(offs, dtype=torch.int64, device=device)
+        self.offsets = offs
+        self.seg_lo = torch.tensor(self.starts, dtype=torch.int64, device=device)
+        self.seg_hi = torch.tensor(self.ends, dtype=torch.int64, device=device)
         self.seg_head = torch.tensor([head_dependency(n) for n in self.names], dtype=torch.int32, device=device)
         module._dc_flat_space = self
 
@@ -65,7 +73,7 @@ class FlatParameterSpace:
 
     def rebind(self):
         """Re-attach ``.grad`` views (``optimizer.zero_grad()`` / ``set_to_none`` detaches them)."""
-        for p, lo, hi in zip(self.params, self.offsets[:-1], self.offsets[1:]):
+        for p, lo, hi in zip(self.params, self.starts, self.ends):
             if p.grad is None or p.grad.data_ptr() != self.grad[lo:hi].data_ptr():
                 p.grad = self.grad[lo:hi].view(p.shape)
 
@@ -75,4 +83,4 @@ class FlatParameterSpace:
 
     def grad_of(self, name):
         i = self.names.index(name)
-        return self.grad[self.offsets[i]:self.offsets[i + 1]].view(self.params[i].shape)
+        return self.grad[self.starts[i]:self.ends[i]].view(self.params[i].shape)

@@ -309,12 +309,13 @@ def grad_flags(flat_grad, total, seg_head, n_actions):
                                      n_actions.data_ptr(), _lib.stream_ptr()), "dc_grad_flags")
 
 
-def grad_finish(flat_param, flat_grad, exp_avg, exp_avg_sq, steps, seg_off, seg_head, total, lr, betas, eps,
+def grad_finish(flat_param, flat_grad, exp_avg, exp_avg_sq, steps, seg_lo, seg_hi, seg_head, total, lr, betas, eps,
                 max_norm, loss_out, metrics, workspace):
     lib = _lib.load()
     with PROFILE.span("grad_finish", 3):
         _lib.check(lib.dc_grad_finish(flat_param.data_ptr(), flat_grad.data_ptr(), exp_avg.data_ptr(),
-                                      exp_avg_sq.data_ptr(), steps.data_ptr(), seg_off.data_ptr(), seg_head.data_ptr(),
+                                      exp_avg_sq.data_ptr(), steps.data_ptr(), seg_lo.data_ptr(), seg_hi.data_ptr(),
+                                      seg_head.data_ptr(),
                                       seg_head.numel(), total, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                       float(max_norm), _lib.ptr(loss_out), metrics.data_ptr(), workspace.data_ptr(),
                                       _lib.stream_ptr()), "dc_grad_finish")

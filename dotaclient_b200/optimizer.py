@@ -486,7 +486,7 @@ class DotaOptimizer:
             ddp.needs_reduction = False
             ddp.auto_reduce = True
         ops.grad_finish(self.flat.param, self.flat.grad_full, self.exp_avg, self.exp_avg_sq, self.adam_steps,
-                        self.flat.seg_off, self.flat.seg_head, self.flat.total, self.learning_rate, self.ADAM_BETAS,
+                        self.flat.seg_lo, self.flat.seg_hi, self.flat.seg_head, self.flat.total, self.learning_rate, self.ADAM_BETAS,
                         self.ADAM_EPS, self.MAX_GRAD_NORM, out, self._metrics, self._finish_ws)     # :674-681
         host = self._host_result
         host[:_lib.LOSS_SLOTS].copy_(out, non_blocking=True)
@@ -506,7 +506,7 @@ class DotaOptimizer:
         """Mean per-tensor L2 norm over parameters that got a gradient in the last step (:691-695)."""
         has = self.flat.flags > 0
         norms = torch.stack([self.flat.grad[lo:hi].norm(2) for lo, hi in
-                             zip(self.flat.offsets[:-1], self.flat.offsets[1:])])
+                             zip(self.flat.starts, self.flat.ends)])
         return norms[has].mean()
 
     # -- iteration driver (:436-579) ----------------------------------------------------------------

@@ -131,7 +131,7 @@ int dc_selected_logp(const float *const logits[DC_NUM_HEADS],
  * x2, clip_grad_norm_(0.5), NaN guard, Adam.step) on ONE flat fp32 buffer holding all params.
  *   flat_grad  [total + n_seg]  gradients, followed by n_seg has-grad counts (after the
  *                               all-reduce: number of ranks that had a gradient, distributed.py:36-37)
- *   seg_off    [n_seg+1] int64  parameter p covers flat elements seg_off[p] .. seg_off[p+1]-1
+ *   seg_lo/hi  [n_seg] int64    parameter p covers flat elements seg_lo[p] .. seg_hi[p]-1 (tensors may be padded apart)
  *   seg_head   [n_seg]   int32  -1 = always has a gradient; h>=0 = has one only if head h took
  *                               an action this batch (optimizer.py:627-630: skipped heads leave
  *                               .grad = None, so Adam and the norm mean skip those tensors)
@@ -144,7 +144,7 @@ int dc_selected_logp(const float *const logits[DC_NUM_HEADS],
 int dc_grad_flags(float *flat_grad, int64_t total, const int32_t *seg_head, int n_seg,
                   const int32_t *n_actions, dc_stream_t stream);
 int dc_grad_finish(float *flat_param, float *flat_grad, float *exp_avg, float *exp_avg_sq,
-                   int32_t *steps, const int64_t *seg_off, const int32_t *seg_head, int n_seg,
+                   int32_t *steps, const int64_t *seg_lo, const int64_t *seg_hi, const int32_t *seg_head, int n_seg,
                    int64_t total, double lr, double beta1, double beta2, double adam_eps,
                    double max_norm, const float *loss_out, float *metrics, void *workspace,
                    dc_stream_t stream);

@@ -51,7 +51,8 @@ def test_gemm_tf32x3_strided_views_and_unsupported_shapes():
     out_big = torch.zeros(500, 256, device=d)
     ops.gemm_tf32x3(a, b, out=out_big[:, 128:])
     ref = (a.double() @ b.double().t())
-    assert (out_big[:, 128:].double() - ref).abs().max().item() < 1e-4
+    scale = (a.double().abs() @ b.double().abs().t()).max().item()
+    assert (out_big[:, 128:].double() - ref).abs().max().item() < 3e-6 * scale
     assert float(out_big[:, :128].abs().sum()) == 0.0
     assert not ops.gemm_tf32x3_supported(100, 100, 128) and not ops.gemm_tf32x3_supported(100, 128, 12)
     with pytest.raises(RuntimeError):
