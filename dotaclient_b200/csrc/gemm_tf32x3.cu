@@ -233,6 +233,193 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
     }
 }
 
+
+// =================================================================================================
+// Weight-gradient GEMM:  dW[No, Ni] = dY[T, No]^T * X[T, Ni]   and   db[No] = column sums of dY.
+//
+// The contraction runs over the TOKEN dimension, so both operands are MN-major in memory (features contiguous).
+// tcgen05 takes them as they are (instruction-descriptor a_major = b_major = MN): a [32 tokens x 128 features] chunk
+// is stored as 4 x 4 swizzle-128B atoms (8 tokens x 32 features each, 1 KB), which is exactly the natural row-major
+// order -- no transposition.  Split-K: the SMs are divided over the (No/128 x Ni/128) output tiles and then over
+// interleaved 32-token chunks; every CTA accumulates a 128x128 fp32 partial in TMEM, writes it to the workspace, and a
+// small second kernel sums the partials in a fixed order (deterministic, unlike atomics).  The producers that stream dY
+// also accumulate its column sums, so the bias gradient costs no extra pass over dY.
+constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
+constexpr int kAtomBytes = 1024;                      // 8 tokens x 32 features x 4 B
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+    // LBO = stride between the four 32-feature atoms of one 8-token group (1 KB); SBO = stride between 8-token groups (4 KB)
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(kAtomBytes >> 4) << 16) | ((uint64_t)(4 * kAtomBytes >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+// Loads tokens [t0, t0+32) x features [f0, f0+128) of a row-major [T, ld] matrix, splits hi/lo and stores MN-major atoms.
+// Returns (through colsum) this thread's running column sums for its 4 features.
+__device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, int ld, int t0, int T, int f0,
+                                                unsigned char *dst_hi, unsigned char *dst_lo, int t, float4 *colsum) {
+    const int l = t & 31, w = t >> 5;                  // lane -> 4 features, warp -> token (mod 4)
+    const int mi = l >> 3, cch = l & 7;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int tok = w + 4 * i;
+        v[i] = (t0 + tok < T) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)(t0 + tok) * ld + f0) + l)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int tok = w + 4 * i;
+        const int row = tok & 7, ki = tok >> 3;
+        const int off = ki * 4 * kAtomBytes + mi * kAtomBytes + row * 128 + ((cch ^ row) << 4);
+        float4 hi, lo;
+        hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
+        lo.x = v[i].x - hi.x; lo.y = v[i].y - hi.y; lo.z = v[i].z - hi.z; lo.w = v[i].w - hi.w;
+        *reinterpret_cast<float4 *>(dst_hi + off) = hi;
+        *reinterpret_cast<float4 *>(dst_lo + off) = lo;
+        if (colsum) { colsum->x += v[i].x; colsum->y += v[i].y; colsum->z += v[i].z; colsum->w += v[i].w; }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__restrict__ dY, int ldy,
+                                                                 const float *__restrict__ X, int ldx, int T, int No, int Ni,
+                                                                 int nsplit, float *__restrict__ part_w,
+                                                                 float *__restrict__ part_b) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
+    uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
+    float *colsum_s = reinterpret_cast<float *>(bars + 2 * kStages + 6);        // [8 warps][128] floats
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
+    const int tile = blockIdx.x % tiles_mn, split = blockIdx.x / tiles_mn;
+    const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+    const int chunks_total = (T + BK - 1) / BK;
+    const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
+        mbar_init(&acc_full[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAccCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kMmaWarp) {
+        // ===== PRODUCERS =====
+        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool want_b = part_b != nullptr && n0 == 0;
+        for (int j = g; j < my_chunks; j += kProducerGroups) {
+            const int stage = j % kStages;
+            const uint32_t phase = (j / kStages) & 1;
+            const int t0 = (split + j * nsplit) * BK;
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char *st = tiles + (size_t)stage * kStageBytes;
+            produce_tile_mn(dY, ldy, t0, T, m0, st, st + kTileBytes, t, want_b ? &cs : nullptr);
+            produce_tile_mn(X, ldx, t0, T, n0, st + 2 * kTileBytes, st + 3 * kTileBytes, t, nullptr);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full[stage]);
+        }
+        if (want_b) *reinterpret_cast<float4 *>(colsum_s + warp * 128 + lane * 4) = cs;
+    } else if (warp == kMmaWarp) {
+        // ===== MMA ISSUER =====
+        for (int j = 0; j < my_chunks; ++j) {
+            const int stage = j % kStages;
+            mbar_wait(&full[stage], (j / kStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t base = smem_u32(tiles + (size_t)stage * kStageBytes);
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {                          // one 8-token group per MMA
+                    const uint32_t adv = ks * 4 * kAtomBytes;
+                    const uint64_t a_hi = make_desc_mn(base + adv), a_lo = make_desc_mn(base + kTileBytes + adv);
+                    const uint64_t b_hi = make_desc_mn(base + 2 * kTileBytes + adv), b_lo = make_desc_mn(base + 3 * kTileBytes + adv);
+                    const uint32_t first = (j | ks) != 0;
+                    umma_tf32(tmem_base, a_lo, b_hi, kIdescMN, first);
+                    umma_tf32(tmem_base, a_hi, b_lo, kIdescMN, 1u);
+                    umma_tf32(tmem_base, a_hi, b_hi, kIdescMN, 1u);
+                }
+                umma_commit(&empty[stage]);
+                if (j == my_chunks - 1) umma_commit(&acc_full[0]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== EPILOGUE: TMEM partial -> workspace [split][tile][128][128] =====
+        const int q = warp & 3;
+        float *prow = part_w + (((size_t)split * tiles_mn + tile) * BM + q * 32 + lane) * BN;
+        if (my_chunks > 0) {
+            mbar_wait(&acc_full[0], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+            uint32_t r[32];
+            if (my_chunks > 0) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4 *>(prow + cb + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (part_b != nullptr && n0 == 0 && threadIdx.x < 128) {         // column sums of this CTA's share of dY
+        float s = 0.f;
+        for (int w = 0; w < kMmaWarp; ++w) s += colsum_s[w * 128 + threadIdx.x];
+        part_b[(size_t)split * No + m0 + threadIdx.x] = s;
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccCols));
+    }
+}
+
+// dW[o][i] (+)= sum_split part_w[split][tile][o%128][i%128];  db[o] (+)= sum_split part_b[split][o]   (fixed order)
+__global__ void wgrad_reduce_kernel(const float *__restrict__ part_w, const float *__restrict__ part_b, int nsplit, int No,
+                                    int Ni, float *__restrict__ dW, int ldw, float *__restrict__ db, int accumulate) {
+    const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // one float4 of dW per thread
+    const int total4 = No * Ni / 4;
+    if (idx < total4) {
+        const int o = (idx * 4) / Ni, i = (idx * 4) % Ni;
+        const int tile = (o / BM) * n_blocks + i / BN;
+        const size_t base = ((size_t)tile * BM + o % BM) * BN + i % BN;
+        float4 acc = accumulate ? *reinterpret_cast<const float4 *>(dW + (size_t)o * ldw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < nsplit; ++s) {
+            const float4 v = *reinterpret_cast<const float4 *>(part_w + (size_t)s * tiles_mn * BM * BN + base);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(dW + (size_t)o * ldw + i) = acc;
+    }
+    if (db != nullptr && idx < No) {
+        float acc = accumulate ? db[idx] : 0.f;
+        for (int s = 0; s < nsplit; ++s) acc += part_b[(size_t)s * No + idx];
+        db[idx] = acc;
+    }
+}
+
 }  // namespace
 
 extern "C" int dc_gemm_tf32x3_supported(int64_t M, int N, int K) { return M > 0 && N > 0 && K > 0 && N % BN == 0 && K % BK == 0; }
@@ -254,6 +441,45 @@ extern "C" int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, 
     const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
     const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
     gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, lda, B, ldb, bias, C, ldc, (int)M, N, K, relu);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+static int wgrad_splits(int No, int Ni) {
+    const int tiles_mn = (No / BM) * (Ni / BN);
+    const int n = dc_sm_count() / tiles_mn;
+    return n < 1 ? 1 : n;
+}
+
+extern "C" size_t dc_gemm_wgrad_workspace_bytes(int No, int Ni) {
+    if (No <= 0 || Ni <= 0 || No % BM || Ni % BN) return 0;
+    const int nsplit = wgrad_splits(No, Ni);
+    return ((size_t)nsplit * No * Ni + (size_t)nsplit * No) * sizeof(float);
+}
+
+extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni, float *dW,
+                                    int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream) {
+    DC_REQUIRE(dY && X && dW && workspace, DC_EINVAL, "dc_gemm_wgrad_tf32x3: null pointer");
+    DC_REQUIRE(T > 0 && T < (1ll << 31) - BK && No > 0 && Ni > 0 && No % BM == 0 && Ni % BN == 0, DC_EUNSUPPORTED,
+               "dc_gemm_wgrad_tf32x3: need No %% 128 == 0 and Ni %% 128 == 0 (T=%lld No=%d Ni=%d)", (long long)T, No, Ni);
+    DC_REQUIRE(ldy >= No && ldx >= Ni && ldw >= Ni && ldy % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0, DC_EINVAL,
+               "dc_gemm_wgrad_tf32x3: bad leading dimension");
+    DC_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)dW & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+               DC_EINVAL, "dc_gemm_wgrad_tf32x3: pointers must be 16-byte aligned");
+    const size_t smem = kSmemBytes + 8 * 128 * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int tiles_mn = (No / BM) * (Ni / BN), nsplit = wgrad_splits(No, Ni);
+    float *part_w = reinterpret_cast<float *>(workspace);
+    float *part_b = db ? part_w + (size_t)nsplit * No * Ni : nullptr;
+    cudaStream_t st = dc_cu_stream(stream);
+    gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ldy, X, ldx, (int)T, No, Ni, nsplit, part_w, part_b);
+    DC_LAUNCH_OK();
+    const int total4 = No * Ni / 4;
+    wgrad_reduce_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);
     DC_LAUNCH_OK();
     return DC_OK;
 }

@@ -396,3 +396,41 @@ def linear(x, weight, bias=None, relu=False):
         return LinearTC.apply(x, weight, bias, relu)
     y = torch.nn.functional.linear(x, weight, bias)
     return torch.relu(y) if relu else y
+
+
+_wgrad_ws = {}
+
+
+def gemm_wgrad_supported(T, No, Ni):
+    return _TC_ENABLED and T > 0 and No % 128 == 0 and Ni % 128 == 0
+
+
+def gemm_wgrad_tf32x3(dy, x, want_bias=True, dw_out=None, db_out=None, accumulate=False):
+    """``dW[No,Ni] = dy[T,No]^T @ x[T,Ni]`` and ``db[No] = dy.sum(0)`` on tcgen05 (3xTF32, split-K, deterministic).
+
+    ``dy`` / ``x`` are 2-D fp32 CUDA tensors with contiguous rows (column-slice views allowed)."""
+    _need_cuda(dy, x)
+    assert dy.dim() == 2 and x.dim() == 2 and dy.shape[0] == x.shape[0]
+    if dy.stride(1) != 1:
+        dy = dy.contiguous()
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    T, No = dy.shape
+    Ni = x.shape[1]
+    dev = dy.device
+    if dw_out is None:
+        dw_out = torch.empty((No, Ni), dtype=torch.float32, device=dev)
+    if want_bias and db_out is None:
+        db_out = torch.empty(No, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    key = (No, Ni, dev)
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        ws = torch.empty(int(lib.dc_gemm_wgrad_workspace_bytes(No, Ni)), dtype=torch.uint8, device=dev)
+        _wgrad_ws[key] = ws
+    with PROFILE.span("gemm_wgrad", 2):
+        _lib.check(lib.dc_gemm_wgrad_tf32x3(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), T, No, Ni,
+                                            dw_out.data_ptr(), dw_out.stride(0), _lib.ptr(db_out) if want_bias else None,
+                                            1 if accumulate else 0, ws.data_ptr(), _lib.stream_ptr()),
+                   "dc_gemm_wgrad_tf32x3")
+    return dw_out, (db_out if want_bias else None)

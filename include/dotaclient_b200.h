@@ -96,6 +96,14 @@ int dc_gemm_tf32x3_supported(int64_t M, int N, int K);
 int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
                    int64_t M, int N, int K, int relu, dc_stream_t stream);
 
+/* Weight gradient of the same layers: dW[No,Ni] (+)= dY[T,No]^T X[T,Ni], db[No] (+)= column sums of dY (NULL = skip).
+ * Replaces the dW/db part of AddmmBackward for those layers (loss.backward(), optimizer.py:672).  Contraction over the
+ * token dimension with MN-major tcgen05 operands, split-K over the SMs, deterministic two-stage reduction.
+ * Requirements: No % 128 == 0, Ni % 128 == 0; workspace of dc_gemm_wgrad_workspace_bytes(No, Ni) bytes. */
+size_t dc_gemm_wgrad_workspace_bytes(int No, int Ni);
+int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni,
+                         float *dW, int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream);
+
 /* ---- fused PPO loss + gradient ----------------------------------------------------------
  * Replaces optimizer.py:587-589 (advantage normalisation) and :621-665 (masked log-softmax x5,
  * ratio, clipped surrogate, entropy, value loss) AND their autograd backward, for N tokens.

@@ -57,3 +57,29 @@ def test_gemm_tf32x3_strided_views_and_unsupported_shapes():
     assert not ops.gemm_tf32x3_supported(100, 100, 128) and not ops.gemm_tf32x3_supported(100, 128, 12)
     with pytest.raises(RuntimeError):
         ops.gemm_tf32x3(torch.randn(10, 12, device=d), torch.randn(128, 12, device=d))
+
+
+@pytest.mark.parametrize("T,No,Ni", [(1, 128, 128), (31, 128, 128), (32, 128, 128), (100, 128, 128), (5000, 128, 128),
+                                     (100000, 128, 128), (4097, 512, 128), (3000, 128, 896), (777, 256, 256)])
+def test_gemm_wgrad_tf32x3_matches_fp64(T, No, Ni):
+    """dW = dY^T X and db = colsum(dY): MN-major tcgen05 operands, split-K over the SMs, deterministic reduction."""
+    from dotaclient_b200 import ops
+    g = torch.Generator().manual_seed(T + No + Ni)
+    dy = torch.randn(T, No, generator=g)
+    x = torch.randn(T, Ni, generator=g)
+    d = torch.device("cuda", 0)
+    dw, db = ops.gemm_wgrad_tf32x3(dy.to(d), x.to(d))
+    ref = dy.double().t() @ x.double()
+    scale = (dy.double().abs().t() @ x.double().abs()).max().item()
+    assert (dw.cpu().double() - ref).abs().max().item() <= 3e-6 * scale
+    refb = dy.double().sum(0)
+    assert (db.cpu().double() - refb).abs().max().item() <= 1e-6 * dy.double().abs().sum(0).max().item() + 1e-6
+    dw2, db2 = ops.gemm_wgrad_tf32x3(dy.to(d), x.to(d))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)            # deterministic
+    # accumulate into an existing gradient, strided views, no bias
+    base = torch.randn(No, Ni, generator=g).to(d)
+    acc = base.clone()
+    big = torch.randn(T, No + 128, generator=g).to(d)
+    ops.gemm_wgrad_tf32x3(big[:, 128:], x.to(d), want_bias=False, dw_out=acc, accumulate=True)
+    ref2 = base.cpu().double() + big[:, 128:].cpu().double().t() @ x.double()
+    assert (acc.cpu().double() - ref2).abs().max().item() <= 3e-6 * max(scale, 1.0) * 4
