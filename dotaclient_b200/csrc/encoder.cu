@@ -1,0 +1,291 @@
+// Memory-bound pieces of the unit encoder and the target-unit attention head (policy.py:99-136,144-153).
+//
+// The 128x128 unit-embedding GEMMs run on the tensor cores (gemm_tf32x3.cu); everything around them is
+// bandwidth work on ~20 KB/token of activations and is written here so that each tensor crosses HBM once:
+//
+//   unit_basic_fwd   relu(units W_b^T + b_b)            [R,12] -> [R,128]     (K = 12: not a tensor-core shape)
+//   unit_basic_bwd   dW_b, db_b from d_basic, the ReLU mask and the raw units  (the inputs need no gradient)
+//   unit_max_fwd     max over the units of a group + argmax (uint8), written straight into the concatenated
+//                    pre-rnn input row (no torch.cat), policy.py:102-136
+//   unit_max_bwd     routes d(max) to the arg-max unit IN PLACE in d(unit embedding): 768 read-modify-writes per
+//                    token instead of three dense [N,40,128] passes (zeros + scatter + add)
+//   target_unit_fwd  logits[n,u] = <attention[n,:], unit_embedding[n,u,:]>      (policy.py:152-153)
+//   target_unit_bwd  d_attention and the rank-1 d(unit embedding)
+//
+// Thread mapping everywhere: one warp per row of 128 channels, lane l owns channels 4l..4l+3 -> every global access
+// is a fully coalesced 512-byte row segment (16 bytes per lane).
+#include "dc_common.cuh"
+
+namespace {
+
+constexpr int kC = 128;          // embedding width (policy.py:56-63)
+constexpr int kIn = 12;          // unit feature count (policy.py:56)
+constexpr int kWarps = 8;
+constexpr int kThreadsE = kWarps * 32;
+constexpr int kMaxUnits = 40;
+
+// ---- relu(units W_b^T + b_b) -------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsE) unit_basic_fwd_kernel(const float *__restrict__ units,
+                                                                   const float *__restrict__ w_b,
+                                                                   const float *__restrict__ b_b,
+                                                                   float *__restrict__ basic, int64_t R) {
+    __shared__ float s_u[kWarps][32][kIn];                        // 32 rows of raw features per warp per iteration
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float w[4][kIn], b[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        b[c] = b_b[lane * 4 + c];
+#pragma unroll
+        for (int k = 0; k < kIn; ++k) w[c][k] = w_b[(lane * 4 + c) * kIn + k];
+    }
+    const int64_t rows_per_iter = (int64_t)gridDim.x * kWarps * 32;
+    for (int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * 32; base < R; base += rows_per_iter) {
+        const int nrows = (int)min((int64_t)32, R - base);
+        // stage 32 x 12 contiguous floats (coalesced), then every lane reads each row as a broadcast
+        float *su = &s_u[warp][0][0];
+        for (int i = lane; i < nrows * kIn; i += 32) su[i] = units[base * kIn + i];
+        __syncwarp();
+        for (int r = 0; r < nrows; ++r) {
+            float acc[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+            for (int k = 0; k < kIn; ++k) {
+                const float u = s_u[warp][r][k];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = fmaf(u, w[c][k], acc[c]);
+            }
+            *reinterpret_cast<float4 *>(basic + (base + r) * kC + lane * 4) =
+                make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+        }
+        __syncwarp();
+    }
+}
+
+// ---- dW_b, db_b ----------------------------------------------------------------------------------
+// partial[block][128][13]: 12 weight-gradient columns + the bias gradient, reduced by a second tiny kernel.
+__global__ void __launch_bounds__(kThreadsE) unit_basic_bwd_kernel(const float *__restrict__ d_basic,
+                                                                   const float *__restrict__ basic,
+                                                                   const float *__restrict__ units, int64_t R,
+                                                                   float *__restrict__ partial) {
+    __shared__ float s_u[kWarps][32][kIn];
+    __shared__ float s_red[kC][kIn + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[4][kIn + 1];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k <= kIn; ++k) acc[c][k] = 0.f;
+    const int64_t rows_per_iter = (int64_t)gridDim.x * kWarps * 32;
+    for (int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * 32; base < R; base += rows_per_iter) {
+        const int nrows = (int)min((int64_t)32, R - base);
+        float *su = &s_u[warp][0][0];
+        for (int i = lane; i < nrows * kIn; i += 32) su[i] = units[base * kIn + i];
+        __syncwarp();
+        for (int r = 0; r < nrows; ++r) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(d_basic + (base + r) * kC) + lane);
+            const float4 y4 = __ldg(reinterpret_cast<const float4 *>(basic + (base + r) * kC) + lane);
+            const float g[4] = {y4.x > 0.f ? g4.x : 0.f, y4.y > 0.f ? g4.y : 0.f, y4.z > 0.f ? g4.z : 0.f, y4.w > 0.f ? g4.w : 0.f};
+#pragma unroll
+            for (int k = 0; k < kIn; ++k) {
+                const float u = s_u[warp][r][k];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c][k] = fmaf(g[c], u, acc[c][k]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c][kIn] += g[c];
+        }
+        __syncwarp();
+    }
+    // fold the 8 warps into one [128][13] tile in a fixed order (deterministic), then one partial per block
+    for (int w = 0; w < kWarps; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int k = 0; k <= kIn; ++k) {
+                    float *dst = &s_red[lane * 4 + c][k];
+                    *dst = (w == 0 ? 0.f : *dst) + acc[c][k];
+                }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < kC * (kIn + 1); i += kThreadsE)
+        partial[(size_t)blockIdx.x * kC * (kIn + 1) + i] = (&s_red[0][0])[i];
+}
+
+__global__ void unit_basic_bwd_reduce_kernel(const float *__restrict__ partial, int nblocks, float *__restrict__ dw_b,
+                                             float *__restrict__ db_b, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // over 128 x 13
+    if (i >= kC * (kIn + 1)) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * kC * (kIn + 1) + i];
+    const int o = i / (kIn + 1), k = i % (kIn + 1);
+    float *dst = k < kIn ? dw_b + o * kIn + k : db_b + o;
+    *dst = accumulate ? *dst + s : s;
+}
+
+// ---- max over the units of one group --------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsE) unit_max_fwd_kernel(const float *__restrict__ emb, int64_t tok_stride,
+                                                                 int units, float *__restrict__ xmax, int ld_x,
+                                                                 float *__restrict__ xmax2, uint8_t *__restrict__ argmax,
+                                                                 int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float4 *row = reinterpret_cast<const float4 *>(emb + n * tok_stride) + lane;
+    float4 best = __ldg(row);
+    uchar4 idx = make_uchar4(0, 0, 0, 0);
+    for (int u = 1; u < units; ++u) {
+        const float4 v = __ldg(row + u * (kC / 4));
+        if (v.x > best.x) { best.x = v.x; idx.x = u; }            // strict >: the first maximum wins, like torch.max
+        if (v.y > best.y) { best.y = v.y; idx.y = u; }
+        if (v.z > best.z) { best.z = v.z; idx.z = u; }
+        if (v.w > best.w) { best.w = v.w; idx.w = u; }
+    }
+    *reinterpret_cast<float4 *>(xmax + n * ld_x + lane * 4) = best;
+    if (xmax2) *reinterpret_cast<float4 *>(xmax2 + n * ld_x + lane * 4) = best;     // policy.py:127: eth slot <- enh max
+    *reinterpret_cast<uchar4 *>(argmax + n * kC + lane * 4) = idx;
+}
+
+__global__ void __launch_bounds__(kThreadsE) unit_max_bwd_kernel(float *__restrict__ d_emb, int64_t tok_stride,
+                                                                 const float *__restrict__ d_xmax,
+                                                                 const float *__restrict__ d_xmax2, int ld_dx,
+                                                                 const uint8_t *__restrict__ argmax, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float4 g = __ldg(reinterpret_cast<const float4 *>(d_xmax + n * ld_dx) + lane);
+    if (d_xmax2) {
+        const float4 g2 = __ldg(reinterpret_cast<const float4 *>(d_xmax2 + n * ld_dx) + lane);
+        g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
+    }
+    const uchar4 idx = *reinterpret_cast<const uchar4 *>(argmax + n * kC + lane * 4);
+    float *base = d_emb + n * tok_stride + lane * 4;
+    base[idx.x * kC + 0] += g.x;
+    base[idx.y * kC + 1] += g.y;
+    base[idx.z * kC + 2] += g.z;
+    base[idx.w * kC + 3] += g.w;
+}
+
+// ---- target-unit attention head ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsE) target_unit_fwd_kernel(const float *__restrict__ att,
+                                                                    const float *__restrict__ ue,
+                                                                    float *__restrict__ logits, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(att + n * kC) + lane);
+    const float4 *row = reinterpret_cast<const float4 *>(ue + n * kMaxUnits * kC) + lane;
+    float mine = 0.f;                                             // lane u keeps logit u (u < 32), lanes 0..7 also u+32
+    float mine_hi = 0.f;
+#pragma unroll 8
+    for (int u = 0; u < kMaxUnits; ++u) {
+        const float4 v = __ldg(row + u * (kC / 4));
+        float d = v.x * a.x + v.y * a.y + v.z * a.z + v.w * a.w;
+        d = dc_warp_sum(d);
+        if (u < 32) { if (lane == u) mine = d; } else { if (lane == u - 32) mine_hi = d; }
+    }
+    logits[n * kMaxUnits + lane] = mine;
+    if (lane < kMaxUnits - 32) logits[n * kMaxUnits + 32 + lane] = mine_hi;
+}
+
+__global__ void __launch_bounds__(kThreadsE) target_unit_bwd_kernel(const float *__restrict__ dlogits,
+                                                                    const float *__restrict__ att,
+                                                                    const float *__restrict__ ue,
+                                                                    float *__restrict__ d_att, float *__restrict__ d_ue,
+                                                                    int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float g_lo = dlogits[n * kMaxUnits + lane];
+    const float g_hi = lane < kMaxUnits - 32 ? dlogits[n * kMaxUnits + 32 + lane] : 0.f;
+    const bool any = __any_sync(0xffffffffu, g_lo != 0.f || g_hi != 0.f);
+    float4 *drow = reinterpret_cast<float4 *>(d_ue + n * kMaxUnits * kC) + lane;
+    float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!any) {                                                   // head unused on this token: exact zeros, no reads
+#pragma unroll 8
+        for (int u = 0; u < kMaxUnits; ++u) drow[u * (kC / 4)] = da;
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(att + n * kC) + lane);
+        const float4 *row = reinterpret_cast<const float4 *>(ue + n * kMaxUnits * kC) + lane;
+#pragma unroll 8
+        for (int u = 0; u < kMaxUnits; ++u) {
+            const float g = __shfl_sync(0xffffffffu, u < 32 ? g_lo : g_hi, u & 31);
+            const float4 v = __ldg(row + u * (kC / 4));
+            da.x = fmaf(g, v.x, da.x); da.y = fmaf(g, v.y, da.y); da.z = fmaf(g, v.z, da.z); da.w = fmaf(g, v.w, da.w);
+            drow[u * (kC / 4)] = make_float4(g * a.x, g * a.y, g * a.z, g * a.w);
+        }
+    }
+    *(reinterpret_cast<float4 *>(d_att + n * kC) + lane) = da;
+}
+
+int grid_rows(int64_t rows_per_block_iter_unused) { (void)rows_per_block_iter_unused; return 4 * dc_sm_count(); }
+
+}  // namespace
+
+extern "C" int dc_unit_basic_fwd(const float *units, const float *w_b, const float *b_b, float *basic, int64_t R,
+                                 dc_stream_t stream) {
+    DC_REQUIRE(units && w_b && b_b && basic && R > 0, DC_EINVAL, "dc_unit_basic_fwd: bad arguments");
+    DC_REQUIRE(((uintptr_t)basic & 15) == 0, DC_EINVAL, "dc_unit_basic_fwd: output must be 16-byte aligned");
+    unit_basic_fwd_kernel<<<grid_rows(0), kThreadsE, 0, dc_cu_stream(stream)>>>(units, w_b, b_b, basic, R);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" size_t dc_unit_basic_bwd_workspace_bytes(void) { return (size_t)4 * 1024 * kC * (kIn + 1) * sizeof(float); }
+
+extern "C" int dc_unit_basic_bwd(const float *d_basic, const float *basic, const float *units, float *dw_b, float *db_b,
+                                 int64_t R, int accumulate, void *workspace, dc_stream_t stream) {
+    DC_REQUIRE(d_basic && basic && units && dw_b && db_b && workspace && R > 0, DC_EINVAL, "dc_unit_basic_bwd: bad arguments");
+    DC_REQUIRE((((uintptr_t)d_basic | (uintptr_t)basic) & 15) == 0, DC_EINVAL, "dc_unit_basic_bwd: inputs must be 16-byte aligned");
+    int blocks = 2 * dc_sm_count();
+    if (blocks > 4 * 1024) blocks = 4 * 1024;
+    cudaStream_t st = dc_cu_stream(stream);
+    float *partial = reinterpret_cast<float *>(workspace);
+    unit_basic_bwd_kernel<<<blocks, kThreadsE, 0, st>>>(d_basic, basic, units, R, partial);
+    DC_LAUNCH_OK();
+    unit_basic_bwd_reduce_kernel<<<(kC * (kIn + 1) + 255) / 256, 256, 0, st>>>(partial, blocks, dw_b, db_b, accumulate);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_unit_max_fwd(const float *emb, int64_t tok_stride, int units, float *xmax, float *xmax_copy, int ld_x,
+                               uint8_t *argmax, int64_t N, dc_stream_t stream) {
+    DC_REQUIRE(emb && xmax && argmax && N > 0 && units >= 1 && units <= 255 && tok_stride >= (int64_t)units * kC, DC_EINVAL,
+               "dc_unit_max_fwd: bad arguments");
+    DC_REQUIRE(((uintptr_t)emb & 15) == 0 && ((uintptr_t)xmax & 15) == 0 && ld_x % 4 == 0 && tok_stride % 4 == 0 &&
+                   (!xmax_copy || ((uintptr_t)xmax_copy & 15) == 0), DC_EINVAL, "dc_unit_max_fwd: alignment");
+    unit_max_fwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(
+        emb, tok_stride, units, xmax, ld_x, xmax_copy, argmax, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_unit_max_bwd(float *d_emb, int64_t tok_stride, const float *d_xmax, const float *d_xmax_copy, int ld_dx,
+                               const uint8_t *argmax, int64_t N, dc_stream_t stream) {
+    DC_REQUIRE(d_emb && d_xmax && argmax && N > 0, DC_EINVAL, "dc_unit_max_bwd: bad arguments");
+    DC_REQUIRE(((uintptr_t)d_xmax & 15) == 0 && ld_dx % 4 == 0 && (!d_xmax_copy || ((uintptr_t)d_xmax_copy & 15) == 0), DC_EINVAL,
+               "dc_unit_max_bwd: alignment");
+    unit_max_bwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(
+        d_emb, tok_stride, d_xmax, d_xmax_copy, ld_dx, argmax, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_target_unit_fwd(const float *att, const float *ue, float *logits, int64_t N, dc_stream_t stream) {
+    DC_REQUIRE(att && ue && logits && N > 0, DC_EINVAL, "dc_target_unit_fwd: bad arguments");
+    DC_REQUIRE((((uintptr_t)att | (uintptr_t)ue) & 15) == 0, DC_EINVAL, "dc_target_unit_fwd: alignment");
+    target_unit_fwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(att, ue, logits, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_target_unit_bwd(const float *dlogits, const float *att, const float *ue, float *d_att, float *d_ue,
+                                  int64_t N, dc_stream_t stream) {
+    DC_REQUIRE(dlogits && att && ue && d_att && d_ue && N > 0, DC_EINVAL, "dc_target_unit_bwd: bad arguments");
+    DC_REQUIRE((((uintptr_t)att | (uintptr_t)ue | (uintptr_t)d_att | (uintptr_t)d_ue) & 15) == 0, DC_EINVAL,
+               "dc_target_unit_bwd: alignment");
+    target_unit_bwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(dlogits, att, ue,
+                                                                                                         d_att, d_ue, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}

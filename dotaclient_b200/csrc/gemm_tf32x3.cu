@@ -238,18 +238,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
 // Weight-gradient GEMM:  dW[No, Ni] = dY[T, No]^T * X[T, Ni]   and   db[No] = column sums of dY.
 //
 // The contraction runs over the TOKEN dimension, so both operands are MN-major in memory (features contiguous).
-// tcgen05 takes them as they are (instruction-descriptor a_major = b_major = MN): a [32 tokens x 128 features] chunk
-// is stored as 4 x 4 swizzle-128B atoms (8 tokens x 32 features each, 1 KB), which is exactly the natural row-major
-// order -- no transposition.  Split-K: the SMs are divided over the (No/128 x Ni/128) output tiles and then over
-// interleaved 32-token chunks; every CTA accumulates a 128x128 fp32 partial in TMEM, writes it to the workspace, and a
-// small second kernel sums the partials in a fixed order (deterministic, unlike atomics).  The producers that stream dY
-// also accumulate its column sums, so the bias gradient costs no extra pass over dY.
+// tcgen05 takes them as they are (instruction-descriptor a_major = b_major = MN).  For 32-bit operands the only
+// MN-major shared-memory layout is SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom): atoms of 4 tokens x 32
+// features (4 rows of 128 B) whose 32-byte chunks are XOR-swizzled with the row index.  A [32 tokens x 128 features]
+// chunk is 8 x 4 such atoms -- the natural row-major order, no transposition.  Split-K: the SMs are divided over the
+// (No/128 x Ni/128) output tiles and then over interleaved 32-token chunks; every CTA accumulates a 128x128 fp32
+// partial in TMEM, writes it to the workspace, and a small second kernel sums the partials in a fixed order
+// (deterministic, unlike atomics).  The producers that stream dY also accumulate its column sums, so the bias
+// gradient costs no extra pass over dY.
 constexpr uint32_t kIdescMN = kIdesc | (1u << 15) | (1u << 16);
-constexpr int kAtomBytes = 1024;                      // 8 tokens x 32 features x 4 B
+constexpr int kAtomBytes = 512;                       // 4 tokens x 32 features x 4 B
+constexpr int kKGroupBytes = 4 * kAtomBytes;          // the four 32-feature atoms of one 4-token group
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
-    // LBO = stride between the four 32-feature atoms of one 8-token group (1 KB); SBO = stride between 8-token groups (4 KB)
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(kAtomBytes >> 4) << 16) | ((uint64_t)(4 * kAtomBytes >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    // LBO = stride between 32-feature atoms (512 B); SBO = stride between 4-token groups (2 KB); layout 1 = SW128_BASE32B
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(kAtomBytes >> 4) << 16) | ((uint64_t)(kKGroupBytes >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
 }
 
 // Loads tokens [t0, t0+32) x features [f0, f0+128) of a row-major [T, ld] matrix, splits hi/lo and stores MN-major atoms.
@@ -257,7 +260,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 __device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, int ld, int t0, int T, int f0,
                                                 unsigned char *dst_hi, unsigned char *dst_lo, int t, float4 *colsum) {
     const int l = t & 31, w = t >> 5;                  // lane -> 4 features, warp -> token (mod 4)
-    const int mi = l >> 3, cch = l & 7;
+    const int mi = l >> 3, c32 = (l & 7) >> 1, half = l & 1;     // 32-feature atom, 32-byte chunk, 16-byte half
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -268,8 +271,8 @@ __device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, i
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int tok = w + 4 * i;
-        const int row = tok & 7, ki = tok >> 3;
-        const int off = ki * 4 * kAtomBytes + mi * kAtomBytes + row * 128 + ((cch ^ row) << 4);
+        const int row = tok & 3, kj = tok >> 2;
+        const int off = kj * kKGroupBytes + mi * kAtomBytes + row * 128 + ((c32 ^ row) << 5) + (half << 4);
         float4 hi, lo;
         hi.x = tf32_rna(v[i].x); hi.y = tf32_rna(v[i].y); hi.z = tf32_rna(v[i].z); hi.w = tf32_rna(v[i].w);
         lo.x = v[i].x - hi.x; lo.y = v[i].y - hi.y; lo.z = v[i].z - hi.z; lo.w = v[i].w - hi.w;
@@ -337,8 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
             if (lane == 0) {
                 const uint32_t base = smem_u32(tiles + (size_t)stage * kStageBytes);
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {                          // one 8-token group per MMA
-                    const uint32_t adv = ks * 4 * kAtomBytes;
+                for (int ks = 0; ks < BK / 8; ++ks) {                          // 8 tokens = two 4-token groups per MMA
+                    const uint32_t adv = ks * 2 * kKGroupBytes;
                     const uint64_t a_hi = make_desc_mn(base + adv), a_lo = make_desc_mn(base + kTileBytes + adv);
                     const uint64_t b_hi = make_desc_mn(base + 2 * kTileBytes + adv), b_lo = make_desc_mn(base + 3 * kTileBytes + adv);
                     const uint32_t first = (j | ks) != 0;
