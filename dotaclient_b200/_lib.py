@@ -26,6 +26,17 @@ SIGNATURES = {
     "dc_gemm_tf32x3": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp]),
     "dc_gemm_wgrad_workspace_bytes": (_sz, [_i32, _i32]),
     "dc_gemm_wgrad_tf32x3": (_i32, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "dc_gemm_tf32x3_blocked": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _vp, _vp, _i32, _i64, _i64, _i64, _i32, _i32, _i32,
+                                      _vp]),
+    "dc_gemm_wgrad_tf32x3_blocked": (_i32, [_vp, _i32, _i64, _i64, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp,
+                                            _vp]),
+    "dc_unit_basic_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "dc_unit_basic_bwd_workspace_bytes": (_sz, []),
+    "dc_unit_basic_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "dc_unit_max_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "dc_unit_max_bwd": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "dc_target_unit_fwd": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "dc_target_unit_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "dc_ppo_loss_fwd_bwd": (_i32, [_ptr5, _ptr5, _ptr5, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _ptr5, _vp, _vp,
                                    _vp, _vp, _vp]),
     "dc_selected_logp": (_i32, [_ptr5, _ptr5, _ptr5, _i64, _vp, _vp]),

@@ -79,16 +79,28 @@ __device__ __forceinline__ float tf32_rna(float v) {
     return __uint_as_float(r);
 }
 
-// Loads rows [row0, row0+128) x cols [k0, k0+32) of a row-major fp32 matrix (ld = leading dim), splits into
+// Row addressing of an operand: plain (row r at r*ld) or two-level (rows grouped in blocks of `rpb` rows that are
+// `bs` floats apart: row r at (r / rpb) * bs + (r % rpb) * ld).  The two-level form lets a GEMM read or write one
+// unit group of the [N, 40, 128] unit-embedding tensor in place (policy.py:130-131's torch.cat disappears).
+struct RowMap {
+    int ld;
+    int rpb;          // 0 = plain
+    long long bs;
+    __device__ __forceinline__ size_t off(int r) const {
+        return rpb > 0 ? (size_t)(r / rpb) * (size_t)bs + (size_t)(r % rpb) * ld : (size_t)r * ld;
+    }
+};
+
+// Loads rows [row0, row0+128) x cols [k0, k0+32) of a row-major fp32 matrix, splits into
 // hi/lo and stores both into K-major swizzle-128B tiles.  Rows >= rows_total are zero-filled.
-__device__ __forceinline__ void produce_tile(const float *__restrict__ src, int ld, int row0, int rows_total, int k0,
+__device__ __forceinline__ void produce_tile(const float *__restrict__ src, RowMap map, int row0, int rows_total, int k0,
                                              unsigned char *dst_hi, unsigned char *dst_lo, int t) {
     const int c = t & 7, r0 = t >> 3;
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + 16 * i;
-        v[i] = (row0 + r < rows_total) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)(row0 + r) * ld + k0) + c)
+        v[i] = (row0 + r < rows_total) ? __ldg(reinterpret_cast<const float4 *>(src + map.off(row0 + r) + k0) + c)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -103,10 +115,10 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ src, int 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *__restrict__ A, int lda,
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *__restrict__ A, RowMap amap,
                                                                   const float *__restrict__ B, int ldb,
                                                                   const float *__restrict__ bias, float *__restrict__ C,
-                                                                  int ldc, int M, int N, int K, int relu) {
+                                                                  RowMap cmap, int M, int N, int K, int relu) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
@@ -143,8 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
                 const uint32_t phase = (chunk / kStages) & 1;
                 mbar_wait(&empty[stage], phase ^ 1);
                 unsigned char *st = tiles + (size_t)stage * kStageBytes;
-                produce_tile(A, lda, m0, M, kc * BK, st, st + kTileBytes, t);
-                produce_tile(B, ldb, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
+                produce_tile(A, amap, m0, M, kc * BK, st, st + kTileBytes, t);
+                produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
                 mbar_arrive(&full[stage]);
             }
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
             mbar_wait(&acc_full[a], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + q * 32 + lane;
-            float *crow = C + (size_t)row * ldc + n0;
+            float *crow = C + cmap.off(row < M ? row : 0) + n0;
 #pragma unroll 1
             for (int cb = 0; cb < BN; cb += 32) {
                 uint32_t r[32];
@@ -257,7 +269,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 
 // Loads tokens [t0, t0+32) x features [f0, f0+128) of a row-major [T, ld] matrix, splits hi/lo and stores MN-major atoms.
 // Returns (through colsum) this thread's running column sums for its 4 features.
-__device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, int ld, int t0, int T, int f0,
+__device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, RowMap map, int t0, int T, int f0,
                                                 unsigned char *dst_hi, unsigned char *dst_lo, int t, float4 *colsum) {
     const int l = t & 31, w = t >> 5;                  // lane -> 4 features, warp -> token (mod 4)
     const int mi = l >> 3, c32 = (l & 7) >> 1, half = l & 1;     // 32-feature atom, 32-byte chunk, 16-byte half
@@ -265,7 +277,7 @@ __device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, i
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int tok = w + 4 * i;
-        v[i] = (t0 + tok < T) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)(t0 + tok) * ld + f0) + l)
+        v[i] = (t0 + tok < T) ? __ldg(reinterpret_cast<const float4 *>(src + map.off(t0 + tok) + f0) + l)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
@@ -282,8 +294,8 @@ __device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, i
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__restrict__ dY, int ldy,
-                                                                 const float *__restrict__ X, int ldx, int T, int No, int Ni,
+__global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__restrict__ dY, RowMap ymap,
+                                                                 const float *__restrict__ X, RowMap xmap, int T, int No, int Ni,
                                                                  int nsplit, float *__restrict__ part_w,
                                                                  float *__restrict__ part_b) {
     extern __shared__ unsigned char smem_raw[];
@@ -325,8 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
             const int t0 = (split + j * nsplit) * BK;
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char *st = tiles + (size_t)stage * kStageBytes;
-            produce_tile_mn(dY, ldy, t0, T, m0, st, st + kTileBytes, t, want_b ? &cs : nullptr);
-            produce_tile_mn(X, ldx, t0, T, n0, st + 2 * kTileBytes, st + 3 * kTileBytes, t, nullptr);
+            produce_tile_mn(dY, ymap, t0, T, m0, st, st + kTileBytes, t, want_b ? &cs : nullptr);
+            produce_tile_mn(X, xmap, t0, T, n0, st + 2 * kTileBytes, st + 3 * kTileBytes, t, nullptr);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full[stage]);
         }
@@ -427,8 +439,9 @@ __global__ void wgrad_reduce_kernel(const float *__restrict__ part_w, const floa
 
 extern "C" int dc_gemm_tf32x3_supported(int64_t M, int N, int K) { return M > 0 && N > 0 && K > 0 && N % BN == 0 && K % BK == 0; }
 
-extern "C" int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
-                              int64_t M, int N, int K, int relu, dc_stream_t stream) {
+static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const float *bias, float *C, RowMap cmap,
+                     int64_t M, int N, int K, int relu, dc_stream_t stream) {
+    const int lda = amap.ld, ldc = cmap.ld;
     DC_REQUIRE(A && B && C, DC_EINVAL, "dc_gemm_tf32x3: null pointer");
     DC_REQUIRE(dc_gemm_tf32x3_supported(M, N, K) && M < (1ll << 31) - BM, DC_EUNSUPPORTED,
                "dc_gemm_tf32x3: need N %% 128 == 0 and K %% 32 == 0 (M=%lld N=%d K=%d)", (long long)M, N, K);
@@ -443,7 +456,7 @@ extern "C" int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, 
     }
     const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
     const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
-    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, lda, B, ldb, bias, C, ldc, (int)M, N, K, relu);
+    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap, (int)M, N, K, relu);
     DC_LAUNCH_OK();
     return DC_OK;
 }
@@ -460,8 +473,9 @@ extern "C" size_t dc_gemm_wgrad_workspace_bytes(int No, int Ni) {
     return ((size_t)nsplit * No * Ni + (size_t)nsplit * No) * sizeof(float);
 }
 
-extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni, float *dW,
-                                    int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream) {
+static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap, int64_t T, int No, int Ni, float *dW,
+                      int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream) {
+    const int ldy = ymap.ld, ldx = xmap.ld;
     DC_REQUIRE(dY && X && dW && workspace, DC_EINVAL, "dc_gemm_wgrad_tf32x3: null pointer");
     DC_REQUIRE(T > 0 && T < (1ll << 31) - BK && No > 0 && Ni > 0 && No % BM == 0 && Ni % BN == 0, DC_EUNSUPPORTED,
                "dc_gemm_wgrad_tf32x3: need No %% 128 == 0 and Ni %% 128 == 0 (T=%lld No=%d Ni=%d)", (long long)T, No, Ni);
@@ -479,10 +493,41 @@ extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, in
     float *part_w = reinterpret_cast<float *>(workspace);
     float *part_b = db ? part_w + (size_t)nsplit * No * Ni : nullptr;
     cudaStream_t st = dc_cu_stream(stream);
-    gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ldy, X, ldx, (int)T, No, Ni, nsplit, part_w, part_b);
+    gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
     DC_LAUNCH_OK();
     const int total4 = No * Ni / 4;
     wgrad_reduce_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);
     DC_LAUNCH_OK();
     return DC_OK;
+}
+
+static bool rowmap_ok(int64_t rpb, int64_t bs, int ld) { return rpb == 0 || (rpb > 0 && rpb < (1 << 30) && bs >= rpb * (int64_t)ld && bs % 4 == 0); }
+
+extern "C" int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
+                              int64_t M, int N, int K, int relu, dc_stream_t stream) {
+    return gemm_impl(A, RowMap{lda, 0, 0}, B, ldb, bias, C, RowMap{ldc, 0, 0}, M, N, K, relu, stream);
+}
+
+// Same GEMM with two-level row addressing of A and/or C (rows_per_block = 0 selects the plain form).
+extern "C" int dc_gemm_tf32x3_blocked(const float *A, int lda, int64_t a_rows_per_block, int64_t a_block_stride,
+                                      const float *B, int ldb, const float *bias, float *C, int ldc,
+                                      int64_t c_rows_per_block, int64_t c_block_stride, int64_t M, int N, int K, int relu,
+                                      dc_stream_t stream) {
+    DC_REQUIRE(rowmap_ok(a_rows_per_block, a_block_stride, lda) && rowmap_ok(c_rows_per_block, c_block_stride, ldc), DC_EINVAL,
+               "dc_gemm_tf32x3_blocked: bad block addressing");
+    return gemm_impl(A, RowMap{lda, (int)a_rows_per_block, (long long)a_block_stride}, B, ldb, bias, C,
+                     RowMap{ldc, (int)c_rows_per_block, (long long)c_block_stride}, M, N, K, relu, stream);
+}
+
+extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni, float *dW,
+                                    int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream) {
+    return wgrad_impl(dY, RowMap{ldy, 0, 0}, X, RowMap{ldx, 0, 0}, T, No, Ni, dW, ldw, db, accumulate, workspace, stream);
+}
+
+extern "C" int dc_gemm_wgrad_tf32x3_blocked(const float *dY, int ldy, int64_t y_rows_per_block, int64_t y_block_stride,
+                                            const float *X, int ldx, int64_t T, int No, int Ni, float *dW, int ldw, float *db,
+                                            int accumulate, void *workspace, dc_stream_t stream) {
+    DC_REQUIRE(rowmap_ok(y_rows_per_block, y_block_stride, ldy), DC_EINVAL, "dc_gemm_wgrad_tf32x3_blocked: bad block addressing");
+    return wgrad_impl(dY, RowMap{ldy, (int)y_rows_per_block, (long long)y_block_stride}, X, RowMap{ldx, 0, 0}, T, No, Ni, dW, ldw,
+                      db, accumulate, workspace, stream);
 }

@@ -1,0 +1,174 @@
+"""Autograd wrappers of the unit encoder and the target-unit head (``policy.py:99-136,144-153``).
+
+Forward and backward are explicit chains of C-ABI kernels -- the fp32-accurate tensor-core GEMMs of
+``csrc/gemm_tf32x3.cu`` for the 128x128 unit embeddings and the bandwidth kernels of ``csrc/encoder.cu`` around them --
+so that every [N, 40, 128] activation crosses HBM once per use: no ``torch.cat`` of the six groups (the GEMMs write and
+read their group's slice of the unit-embedding tensor in place), no dense zeros+scatter+add for the max-pool backward.
+"""
+import torch
+
+from . import _lib
+from .ops import PROFILE, _f32c, _need_cuda, gemm_wgrad_supported
+
+UNITS = (1, 5, 16, 16, 1, 1)              # allied/enemy heroes, allied/enemy non-heroes, allied/enemy towers
+OFFSETS = (0, 1, 6, 22, 38, 39)
+MAX_UNITS = 40
+C = 128
+TOK = MAX_UNITS * C                        # floats per token in the unit-embedding tensor
+
+_basic_ws = {}
+
+
+def _basic_workspace(device):
+    ws = _basic_ws.get(device)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().dc_unit_basic_bwd_workspace_bytes()), dtype=torch.uint8, device=device)
+        _basic_ws[device] = ws
+    return ws
+
+
+_wgrad_ws = {}
+
+
+def _wgrad_workspace(No, Ni, device):
+    key = (No, Ni, device)
+    ws = _wgrad_ws.get(key)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().dc_gemm_wgrad_workspace_bytes(No, Ni)), dtype=torch.uint8, device=device)
+        _wgrad_ws[key] = ws
+    return ws
+
+
+def _ptr(t, float_offset=0):
+    return t.data_ptr() + 4 * float_offset
+
+
+class UnitEncoder(torch.autograd.Function):
+    """(w_b, b_b, units x6, W_g x6, b_g x6) -> unit embedding ``[..., 40, 128]`` and the six group maxima ``[..., 768]``.
+
+    maxima slot 5 (enemy towers) is a copy of slot 3 (enemy non-heroes): the reference's ``policy.py:127``.
+    """
+
+    @staticmethod
+    def forward(ctx, w_b, b_b, *rest):
+        units, weights, biases = rest[:6], rest[6:12], rest[12:18]
+        _need_cuda(w_b, *units)
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        lead = units[0].shape[:-2]
+        N = 1
+        for d in lead:
+            N *= d
+        dev = units[0].device
+        w_b, b_b = _f32c(w_b.detach()), _f32c(b_b.detach())
+        units = [_f32c(u.detach()).reshape(N * n, 12) for u, n in zip(units, UNITS)]
+        weights = [_f32c(w.detach()) for w in weights]
+        biases = [_f32c(b.detach()) for b in biases]
+        ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
+        xm = torch.empty((N, 6 * C), dtype=torch.float32, device=dev)
+        argmax = torch.empty((5, N, C), dtype=torch.uint8, device=dev)
+        basics = []
+        for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
+            R = N * n_u
+            basic = torch.empty((R, C), dtype=torch.float32, device=dev)
+            with PROFILE.span("unit_basic_fwd", 1):
+                _lib.check(lib.dc_unit_basic_fwd(units[g].data_ptr(), w_b.data_ptr(), b_b.data_ptr(), basic.data_ptr(), R, st),
+                           "dc_unit_basic_fwd")
+            with PROFILE.span("gemm_tf32x3", 1):
+                _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, weights[g].data_ptr(), C, biases[g].data_ptr(),
+                                                      _ptr(ue, off * C), C, n_u, TOK, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
+            if g < 5:
+                copy = _ptr(xm, 5 * C) if g == 3 else None
+                with PROFILE.span("unit_max_fwd", 1):
+                    _lib.check(lib.dc_unit_max_fwd(_ptr(ue, off * C), TOK, n_u, _ptr(xm, g * C), copy, 6 * C,
+                                                   argmax[g].data_ptr(), N, st), "dc_unit_max_fwd")
+            basics.append(basic)
+        ctx.N = N
+        ctx.lead = lead
+        ctx.save_for_backward(argmax, *units, *basics, *weights)
+        return ue.view(*lead, MAX_UNITS, C), xm.view(*lead, 6 * C)
+
+    @staticmethod
+    def backward(ctx, d_ue, d_xm):
+        saved = ctx.saved_tensors
+        argmax, units, basics, weights = saved[0], saved[1:7], saved[7:13], saved[13:19]
+        N = ctx.N
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        dev = argmax.device
+        if d_ue is None:
+            d_ue = torch.zeros((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
+        else:
+            d_ue = _f32c(d_ue).reshape(N, MAX_UNITS, C)          # modified in place below (sole consumer)
+        if d_xm is not None:
+            d_xm = _f32c(d_xm).reshape(N, 6 * C)
+            for g in range(5):
+                copy = _ptr(d_xm, 5 * C) if g == 3 else None
+                with PROFILE.span("unit_max_bwd", 1):
+                    _lib.check(lib.dc_unit_max_bwd(_ptr(d_ue, OFFSETS[g] * C), TOK, _ptr(d_xm, g * C), copy, 6 * C,
+                                                   argmax[g].data_ptr(), N, st), "dc_unit_max_bwd")
+        dw_b = torch.empty((C, 12), dtype=torch.float32, device=dev)
+        db_b = torch.empty(C, dtype=torch.float32, device=dev)
+        d_basic = torch.empty((N * max(UNITS), C), dtype=torch.float32, device=dev)
+        ws_w = _wgrad_workspace(C, C, dev)
+        ws_b = _basic_workspace(dev)
+        dws, dbs = [], []
+        for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
+            R = N * n_u
+            dw = torch.empty((C, C), dtype=torch.float32, device=dev)
+            db = torch.empty(C, dtype=torch.float32, device=dev)
+            with PROFILE.span("gemm_wgrad", 2):        # dW_g = d_emb_g^T basic_g, db_g = colsum(d_emb_g)
+                _lib.check(lib.dc_gemm_wgrad_tf32x3_blocked(_ptr(d_ue, off * C), C, n_u, TOK, basics[g].data_ptr(), C, R, C, C,
+                                                            dw.data_ptr(), C, db.data_ptr(), 0, ws_w.data_ptr(), st),
+                           "dc_gemm_wgrad_tf32x3_blocked")
+            wt = weights[g].t().contiguous()
+            with PROFILE.span("gemm_tf32x3", 1):       # d_basic_g = d_emb_g W_g
+                _lib.check(lib.dc_gemm_tf32x3_blocked(_ptr(d_ue, off * C), C, n_u, TOK, wt.data_ptr(), C, None,
+                                                      d_basic.data_ptr(), C, 0, 0, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
+            with PROFILE.span("unit_basic_bwd", 2):    # through the ReLU into W_b, b_b (shared by the six groups)
+                _lib.check(lib.dc_unit_basic_bwd(d_basic.data_ptr(), basics[g].data_ptr(), units[g].data_ptr(), dw_b.data_ptr(),
+                                                 db_b.data_ptr(), R, 1 if g > 0 else 0, ws_b.data_ptr(), st), "dc_unit_basic_bwd")
+            dws.append(dw)
+            dbs.append(db)
+        return (dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
+
+
+class TargetUnit(torch.autograd.Function):
+    """``logits[..., u] = <attention[..., :], unit_embedding[..., u, :]>`` (``policy.py:152-153``)."""
+
+    @staticmethod
+    def forward(ctx, att, ue):
+        _need_cuda(att, ue)
+        lead = att.shape[:-1]
+        N = att.numel() // C
+        att2, ue2 = _f32c(att.detach()).reshape(N, C), _f32c(ue.detach()).reshape(N, MAX_UNITS, C)
+        logits = torch.empty((N, MAX_UNITS), dtype=torch.float32, device=att.device)
+        with PROFILE.span("target_unit_fwd", 1):
+            _lib.check(_lib.load().dc_target_unit_fwd(att2.data_ptr(), ue2.data_ptr(), logits.data_ptr(), N, _lib.stream_ptr()),
+                       "dc_target_unit_fwd")
+        ctx.save_for_backward(att2, ue2)
+        ctx.shapes = (att.shape, ue.shape)
+        return logits.view(*lead, MAX_UNITS)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        att2, ue2 = ctx.saved_tensors
+        N = att2.shape[0]
+        dl = _f32c(dlogits).reshape(N, MAX_UNITS)
+        d_att = torch.empty_like(att2)
+        d_ue = torch.empty_like(ue2)
+        with PROFILE.span("target_unit_bwd", 1):
+            _lib.check(_lib.load().dc_target_unit_bwd(dl.data_ptr(), att2.data_ptr(), ue2.data_ptr(), d_att.data_ptr(),
+                                                      d_ue.data_ptr(), N, _lib.stream_ptr()), "dc_target_unit_bwd")
+        return d_att.view(ctx.shapes[0]), d_ue.view(ctx.shapes[1])
+
+
+def unit_encoder(w_b, b_b, units, weights, biases):
+    return UnitEncoder.apply(w_b, b_b, *units, *weights, *biases)
+
+
+def target_unit(att, ue):
+    return TargetUnit.apply(att, ue)
+
+
+__all__ = ["unit_encoder", "target_unit", "gemm_wgrad_supported"]

@@ -232,17 +232,26 @@ class RnnSequence(torch.autograd.Function):
                 dx = gemm_tf32x3(dgi, w_ih.t().contiguous()).view(S, B, Hin)     # dx = dgi W_ih on tcgen05
             else:
                 dx = torch.mm(dgi, w_ih).view(S, B, Hin)
-            dw_ih = torch.mm(dgi.t(), x2)
-            db_ih = dgi.sum(0)
+            tc = gemm_wgrad_supported(N, G * H, Hin) and gemm_wgrad_supported(N, G * H, H) and H % 128 == 0
+            if tc:
+                dw_ih, db_ih = gemm_wgrad_tf32x3(dgi, x2)                         # dW_ih = dgi^T x, db_ih = colsum(dgi)
+            else:
+                dw_ih = torch.mm(dgi.t(), x2)
+                db_ih = dgi.sum(0)
             if cell == "lstm":
-                dw_hh = torch.mm(dgi.t(), hprev)
+                dw_hh = gemm_wgrad_tf32x3(dgi, hprev, want_bias=False)[0] if tc else torch.mm(dgi.t(), hprev)
                 db_hh = db_ih
             else:
                 dghn = cbuf[1:].view(N, H)            # n-gate part of dgh (= dgi_n * r)
                 dw_hh = torch.empty_like(w_hh)
-                torch.mm(dgi[:, :2 * H].t(), hprev, out=dw_hh[:2 * H])
-                torch.mm(dghn.t(), hprev, out=dw_hh[2 * H:])
-                db_hh = torch.cat([db_ih[:2 * H], dghn.sum(0)])
+                if tc:
+                    gemm_wgrad_tf32x3(dgi[:, :2 * H], hprev, want_bias=False, dw_out=dw_hh[:2 * H])
+                    _, db_n = gemm_wgrad_tf32x3(dghn, hprev, dw_out=dw_hh[2 * H:])
+                else:
+                    torch.mm(dgi[:, :2 * H].t(), hprev, out=dw_hh[:2 * H])
+                    torch.mm(dghn.t(), hprev, out=dw_hh[2 * H:])
+                    db_n = dghn.sum(0)
+                db_hh = torch.cat([db_ih[:2 * H], db_n])
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev
         return dx, dw_ih, dw_hh, db_ih, db_hh, dh0, dc0, None
@@ -384,8 +393,11 @@ class LinearTC(torch.autograd.Function):
             else:
                 dx = dy2 @ w
             dx = dx.view(*dy.shape[:-1], K)
-        dw = torch.mm(dy2.t(), x2) if ctx.needs_input_grad[1] else None
-        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        if ctx.needs_input_grad[1] and gemm_wgrad_supported(dy2.shape[0], N, K):
+            dw, db = gemm_wgrad_tf32x3(dy2, x2, want_bias=ctx.has_bias)     # dW = dy^T x, db = colsum(dy), one pass over dy
+        else:
+            dw = torch.mm(dy2.t(), x2) if ctx.needs_input_grad[1] else None
+            db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
 

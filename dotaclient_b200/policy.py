@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import encoder_ops, ops
 
 logger = logging.getLogger(__name__)
 
@@ -117,6 +117,14 @@ class Policy(nn.Module):
     # ------------------------------------------------------------------ implementation
     def _encode(self, env, groups):
         """Observation encoders (``policy.py:97-138``) -> (x ``[..., H]``, unit embedding ``[..., 40, 128]``)."""
+        if ops._TC_ENABLED and env.is_cuda:
+            # explicit kernel chain (csrc/encoder.cu + tcgen05 GEMMs): no torch.cat, sparse max-pool backward
+            layers = [getattr(self, "affine_unit_" + s) for s, _, _ in UNIT_GROUPS]
+            unit_embedding, xmax = encoder_ops.unit_encoder(
+                self.affine_unit_basic_stats.weight, self.affine_unit_basic_stats.bias, list(groups),
+                [l.weight for l in layers], [l.bias for l in layers])
+            x = torch.cat([F.relu(self.affine_env(env)), xmax], dim=-1)
+            return ops.linear(x, self.affine_pre_rnn.weight, self.affine_pre_rnn.bias, relu=True), unit_embedding
         emb, emb_max = {}, {}
         for (suffix, _, _), units in zip(UNIT_GROUPS, groups):
             basic = F.relu(self.affine_unit_basic_stats(units))
@@ -146,7 +154,10 @@ class Policy(nn.Module):
         move_x = self.affine_move_x(y)
         move_y = self.affine_move_y(y)
         head_enum = self.affine_head_enum(y)
-        target_unit = torch.matmul(attention, unit_embedding.transpose(-1, -2)).squeeze(-2)
+        if ops._TC_ENABLED and y.is_cuda:
+            target_unit = encoder_ops.target_unit(attention.squeeze(-2), unit_embedding)
+        else:
+            target_unit = torch.matmul(attention, unit_embedding.transpose(-1, -2)).squeeze(-2)
         ability = self.affine_head_ability(y)
         value = self.affine_value(y)
         return {'enum': head_enum, 'x': move_x, 'y': move_y, 'target_unit': target_unit, 'ability': ability}, value

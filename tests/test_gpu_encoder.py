@@ -1,0 +1,85 @@
+"""GPU tests of the unit-encoder kernel chain and the target-unit head against plain torch on the CPU
+(the same ops the oracle's ``RefPolicy.forward`` performs, ``policy.py:99-136,144-153``).
+
+Tolerances: fp32 kernels + 3xTF32 tensor-core GEMMs vs fp32 CPU: forward atol 2e-5 on O(1) activations,
+gradients rtol 2e-4 with an absolute floor scaled by the token count (sums over tokens)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+UNITS = (1, 5, 16, 16, 1, 1)
+
+
+def _reference(w_b, b_b, units, weights, biases):
+    emb = [F.linear(F.relu(F.linear(u, w_b, b_b)), w, b) for u, w, b in zip(units, weights, biases)]
+    mx = [e.max(dim=-2)[0] for e in emb]
+    mx[5] = mx[3]                                        # policy.py:127
+    return torch.cat(emb, dim=-2), torch.cat(mx, dim=-1)
+
+
+@pytest.mark.parametrize("lead", [(7,), (3, 5), (1,), (130,)])
+def test_unit_encoder_forward_backward(lead):
+    from dotaclient_b200 import encoder_ops
+    g = torch.Generator().manual_seed(sum(lead))
+    w_b = (torch.randn(128, 12, generator=g) * 0.3).requires_grad_(True)
+    b_b = (torch.randn(128, generator=g) * 0.1).requires_grad_(True)
+    units = [torch.randn(*lead, n, 12, generator=g) for n in UNITS]
+    weights = [(torch.randn(128, 128, generator=g) * 0.1).requires_grad_(True) for _ in UNITS]
+    biases = [(torch.randn(128, generator=g) * 0.1).requires_grad_(True) for _ in UNITS]
+    ue_r, xm_r = _reference(w_b, b_b, units, weights, biases)
+    g_ue = torch.randn(ue_r.shape, generator=g)
+    g_xm = torch.randn(xm_r.shape, generator=g)
+    ((ue_r * g_ue).sum() + (xm_r * g_xm).sum()).backward()
+
+    d = torch.device("cuda", 0)
+    params = [t.detach().clone().to(d).requires_grad_(True) for t in [w_b, b_b] + weights + biases]
+    ue, xm = encoder_ops.unit_encoder(params[0], params[1], [u.to(d) for u in units], params[2:8], params[8:14])
+    assert ue.shape == ue_r.shape and xm.shape == xm_r.shape
+    torch.testing.assert_close(ue.detach().cpu(), ue_r.detach(), rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(xm.detach().cpu(), xm_r.detach(), rtol=1e-4, atol=2e-5)
+    ((ue * g_ue.to(d)).sum() + (xm * g_xm.to(d)).sum()).backward()
+    n_tok = ue_r.numel() // (40 * 128)
+    for mine, ref in zip(params, [w_b, b_b] + weights + biases):
+        torch.testing.assert_close(mine.grad.cpu(), ref.grad, rtol=2e-4, atol=2e-6 * max(1, n_tok) * 16)
+
+
+def test_unit_max_tie_breaking_and_grad_routing():
+    """Equal maxima: the FIRST unit wins (torch.max semantics on CPU) and receives the whole gradient."""
+    from dotaclient_b200 import encoder_ops
+    d = torch.device("cuda", 0)
+    w_b = torch.zeros(128, 12)
+    b_b = torch.ones(128)                                 # basic == 1 for every unit -> all units tie
+    units = [torch.randn(4, n, 12) for n in UNITS]
+    weights = [torch.eye(128) for _ in UNITS]
+    biases = [torch.zeros(128) for _ in UNITS]
+    params = [t.to(d).requires_grad_(True) for t in [w_b, b_b] + weights + biases]
+    ue, xm = encoder_ops.unit_encoder(params[0], params[1], [u.to(d) for u in units], params[2:8], params[8:14])
+    assert torch.equal(xm, torch.ones_like(xm))
+    ue.retain_grad()
+    xm.sum().backward()
+    # bias gradient of group g == number of tokens routed to it: only unit 0 of each group gets d(max)
+    for gidx in range(5):
+        expect = 4.0 * (2.0 if gidx == 3 else 1.0)         # enh also receives the enemy-tower slot's gradient
+        assert torch.allclose(params[8 + gidx].grad.cpu(), torch.full((128,), expect))
+    assert float(params[13].grad.abs().sum()) == 0.0      # eth: no path from the maxima (policy.py:127)
+
+
+@pytest.mark.parametrize("lead", [(9,), (4, 6), (257,)])
+def test_target_unit_forward_backward(lead):
+    from dotaclient_b200 import encoder_ops
+    g = torch.Generator().manual_seed(len(lead) + lead[0])
+    att = torch.randn(*lead, 128, generator=g).requires_grad_(True)
+    ue = torch.randn(*lead, 40, 128, generator=g).requires_grad_(True)
+    ref = torch.matmul(att.unsqueeze(-2), ue.transpose(-1, -2)).squeeze(-2)
+    go = torch.randn(ref.shape, generator=g)
+    go[..., ::3, :] = 0                                    # tokens where the head was not used: exact-zero rows
+    (ref * go).sum().backward()
+    d = torch.device("cuda", 0)
+    a2, u2 = att.detach().to(d).requires_grad_(True), ue.detach().to(d).requires_grad_(True)
+    out = encoder_ops.target_unit(a2, u2)
+    torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=1e-5)
+    (out * go.to(d)).sum().backward()
+    torch.testing.assert_close(a2.grad.cpu(), att.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(u2.grad.cpu(), ue.grad, rtol=1e-6, atol=1e-6)
