@@ -72,6 +72,8 @@ def measured_peak_hbm():
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
 def log(msg):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
     sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - _T0, msg))
     sys.stderr.flush()
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreadsE) unit_basic_fwd_kernel(const float *
 
 // ---- dW_b, db_b ----------------------------------------------------------------------------------
 // partial[block][128][13]: 12 weight-gradient columns + the bias gradient, reduced by a second tiny kernel.
-__global__ void __launch_bounds__(kThreadsE) unit_basic_bwd_kernel(const float *__restrict__ d_basic,
+__global__ void __launch_bounds__(kThreadsE, 2) unit_basic_bwd_kernel(const float *__restrict__ d_basic,
                                                                    const float *__restrict__ basic,
                                                                    const float *__restrict__ units, int64_t R,
                                                                    float *__restrict__ partial) {
@@ -80,18 +80,28 @@ __global__ void __launch_bounds__(kThreadsE) unit_basic_bwd_kernel(const float *
         float *su = &s_u[warp][0][0];
         for (int i = lane; i < nrows * kIn; i += 32) su[i] = units[base * kIn + i];
         __syncwarp();
-        for (int r = 0; r < nrows; ++r) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(d_basic + (base + r) * kC) + lane);
-            const float4 y4 = __ldg(reinterpret_cast<const float4 *>(basic + (base + r) * kC) + lane);
-            const float g[4] = {y4.x > 0.f ? g4.x : 0.f, y4.y > 0.f ? g4.y : 0.f, y4.z > 0.f ? g4.z : 0.f, y4.w > 0.f ? g4.w : 0.f};
+        for (int r0 = 0; r0 < nrows; r0 += 4) {      // 4 rows per trip: 8 independent 16-byte loads in flight per lane
+            float4 g4[4], y4[4];
 #pragma unroll
-            for (int k = 0; k < kIn; ++k) {
-                const float u = s_u[warp][r][k];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c][k] = fmaf(g[c], u, acc[c][k]);
+            for (int j = 0; j < 4; ++j) {
+                const int r = min(r0 + j, nrows - 1);
+                g4[j] = __ldg(reinterpret_cast<const float4 *>(d_basic + (base + r) * kC) + lane);
+                y4[j] = __ldg(reinterpret_cast<const float4 *>(basic + (base + r) * kC) + lane);
             }
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[c][kIn] += g[c];
+            for (int j = 0; j < 4; ++j) {
+                if (r0 + j >= nrows) break;
+                const float g[4] = {y4[j].x > 0.f ? g4[j].x : 0.f, y4[j].y > 0.f ? g4[j].y : 0.f,
+                                    y4[j].z > 0.f ? g4[j].z : 0.f, y4[j].w > 0.f ? g4[j].w : 0.f};
+#pragma unroll
+                for (int k = 0; k < kIn; ++k) {
+                    const float u = s_u[warp][r0 + j][k];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c][k] = fmaf(g[c], u, acc[c][k]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c][kIn] += g[c];
+            }
         }
         __syncwarp();
     }

@@ -31,7 +31,7 @@ constexpr int kStages = 3;
 constexpr int kTileBytes = BM * BK * 4;              // 16 KB
 constexpr int kStageBytes = 4 * kTileBytes;          // A_hi, A_lo, B_hi, B_lo
 constexpr int kProducerThreads = 128;
-constexpr int kProducerGroups = 2;
+constexpr int kProducerGroups = 3;
 constexpr int kMmaWarp = 4 * kProducerGroups;
 constexpr int kThreads = (kMmaWarp + 1 + 4) * 32;
 constexpr int kAccCols = 128, kTmemCols = 256;       // two accumulator buffers
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
     uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
-    float *colsum_s = reinterpret_cast<float *>(bars + 2 * kStages + 6);        // [8 warps][128] floats
+    float *colsum_s = reinterpret_cast<float *>(bars + 2 * kStages + 6);        // [producer warps][128] floats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
@@ -483,7 +483,7 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
                "dc_gemm_wgrad_tf32x3: bad leading dimension");
     DC_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)dW & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
                DC_EINVAL, "dc_gemm_wgrad_tf32x3: pointers must be 16-byte aligned");
-    const size_t smem = kSmemBytes + 8 * 128 * sizeof(float);
+    const size_t smem = kSmemBytes + kMmaWarp * 128 * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
