@@ -5,6 +5,15 @@
 #include "dc_common.cuh"
 #include "rnn_generic.cuh"
 #include "rnn_resident.cuh"
+#include "rnn_resident2.cuh"
+#include <cstdlib>
+
+// DC_RNN_V1=1 selects the first-generation (two barriers per step) resident kernels, for A/B measurements.
+static bool use_v1() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("DC_RNN_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 
 extern "C" size_t dc_rnn_workspace_bytes(int cell, int H) {
     const int G = cell == DC_CELL_GRU ? 3 : 4;
@@ -25,7 +34,9 @@ extern "C" int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const f
     DC_REQUIRE(gates && w_hh && b_hh && ybuf && cbuf && workspace, DC_EINVAL, "dc_rnn_seq_fwd: null pointer");
     cudaStream_t st = dc_cu_stream(stream);
     const int G = cell == DC_CELL_GRU ? 3 : 4;
-    // both forward kernels read W_hh^T [H, G*H] so that output columns are contiguous (coalesced / float4)
+    if (dc_rnn::resident_supported(cell, H) && !use_v1())
+        return dc_rnn2::launch_fwd(cell, gates, w_hh, b_hh, ybuf, cbuf, B, S, st);   // reads W_hh as stored
+    // the other forward kernels read W_hh^T [H, G*H] so that output columns are contiguous (coalesced / float4)
     float *wT = reinterpret_cast<float *>(workspace);
     dim3 tb(32, 8), tg((H + 31) / 32, (G * H + 31) / 32);
     dc_rnn::transpose_kernel<<<tg, tb, 0, st>>>(w_hh, wT, G * H, H);
@@ -53,6 +64,8 @@ extern "C" int dc_rnn_seq_bwd(int cell, float *gates, const float *w_hh, const f
     DC_REQUIRE(gates && w_hh && ybuf && cbuf && dy, DC_EINVAL, "dc_rnn_seq_bwd: null pointer");
     cudaStream_t st = dc_cu_stream(stream);
     const int G = cell == DC_CELL_GRU ? 3 : 4;
+    if (dc_rnn::resident_supported(cell, H) && !use_v1())
+        return dc_rnn2::launch_bwd(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st);
     if (dc_rnn::resident_supported(cell, H))
         return dc_rnn::launch_bwd_resident(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, H, st);
     const int blocks = (B + dc_rnn::kBT - 1) / dc_rnn::kBT;
