@@ -31,6 +31,9 @@ CONFIGS = {                       # BASELINE.json configs; batch is PER GPU
     "c2": dict(batch=256, seq_len=512, hidden=128, cell="lstm"),
     "c3": dict(batch=512, seq_len=512, hidden=256, cell="lstm"),
     "c4": dict(batch=512, seq_len=1024, hidden=512, cell="lstm"),
+    # configs[4]: 40-agent replay stream through the in-process broker, the reference's own defaults
+    # (optimizer.py:781-786: min_seq_per_epoch 1024, seq_len 16, epochs 4; policy.py:66: 256-wide GRU)
+    "c5": dict(batch=1024, seq_len=16, hidden=256, cell="gru", stream=True),
 }
 FALLBACK_HBM_GBS = 6650.0         # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -208,9 +211,80 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def run_stream(args, cfg):
+    """BASELINE configs[4]: 40 agents (threads) publish pickled rollouts of 1000-1400 steps into the in-process
+    ``MessageQueue``; every rank runs ``DotaOptimizer.run_iteration`` (pull -> prep -> epochs x train -> publish) and
+    steady-state optimizer steps/s is reported.  Secondary configuration (not the headline bench line)."""
+    import pickle
+    import random
+    import torch
+    import torch.distributed as dist
+    from dotaclient_b200.optimizer import DotaOptimizer, MessageQueue
+    from dotaclient_b200.synthetic import make_rollout
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl")
+    epochs = 4
+    opt = DotaOptimizer(rmq_host="stream", rmq_port=rank, epochs=epochs, min_seq_per_epoch=cfg["batch"], seq_len=cfg["seq_len"],
+                        learning_rate=5e-5, checkpoint=False, pretrained_model=None, mq_prefetch_count=1,
+                        log_dir=tempfile.mkdtemp(), entropy_coef=5e-4, vf_coef=0.5, run_local=True,
+                        hidden_size=cfg["hidden"], cell=cfg["cell"])
+    agents = max(1, 40 // world)
+    rng = random.Random(7 + rank)
+    pool = [pickle.dumps(make_rollout(rng.randint(1000, 1400), 7 + 1000 * rank + i, with_canvas=True)) for i in range(8)]
+    stop = threading.Event()
+    mq = MessageQueue(host="stream", port=rank, prefetch_count=1, use_model_exchange=False)
+    mq.connect()
+
+    def agent(i):
+        j = i
+        while not stop.is_set():
+            if mq.xp_queue_size < 64:
+                mq.publish_experience(pool[j % len(pool)])
+                j += 1
+            else:
+                time.sleep(0.001)
+    threads = [threading.Thread(target=agent, args=(i,), daemon=True) for i in range(agents)]
+    for th in threads:
+        th.start()
+    for it in range(1, 1 + max(1, args.warmup)):
+        opt.run_iteration(it)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    env_steps = 0
+    for it in range(args.steps):
+        m = opt.run_iteration(100 + it)
+        env_steps += int(round(m[opt.SPEED_KEY] * m["timing/it"]))
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], device="cuda")
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    stop.set()
+    if rank == 0:
+        sec = float(el.item())
+        print(json.dumps({"metric": "optimizer_steps_per_sec", "value": world * args.steps * epochs / sec, "unit": "steps/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": 1000 * sec / (args.steps * epochs),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "env_steps_per_sec": world * env_steps / sec,
+                          "config": {"workload": "BASELINE configs[4]: 40-agent replay stream, in-process broker, reference defaults "
+                                                 "(>=1024 seqs x 16 per iteration, 4 epochs, hidden 256 GRU); 'step' = one train() call "
+                                                 "including its share of experience prep", "agents": agents * world,
+                                     "parallelism": "dp%d" % world}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     cfg = resolve_config(args)
+    if cfg.get("stream"):
+        run_stream(args, cfg)
+        return
     if args.impl == "reference":
         run_reference_arm(args, cfg)
         return

@@ -91,18 +91,22 @@ struct RowMap {
     }
 };
 
-// Loads rows [row0, row0+128) x cols [k0, k0+32) of a row-major fp32 matrix, splits into
-// hi/lo and stores both into K-major swizzle-128B tiles.  Rows >= rows_total are zero-filled.
-__device__ __forceinline__ void produce_tile(const float *__restrict__ src, RowMap map, int row0, int rows_total, int k0,
-                                             unsigned char *dst_hi, unsigned char *dst_lo, int t) {
+// K-major operand chunk: rows [row0, row0+128) x cols [k0, k0+32) of a row-major fp32 matrix.  tile_load_k issues the
+// eight 16-byte loads of this thread (rows >= rows_total read as zero); tile_store_k splits hi/lo and stores both
+// swizzle-128B tiles.  Keeping the two halves apart lets a producer issue the NEXT chunk's loads before it touches the
+// current chunk's data (register double buffering), which hides the global-load latency ncu showed as 64 % long-scoreboard.
+__device__ __forceinline__ void tile_load_k(const float *__restrict__ src, RowMap map, int row0, int rows_total, int k0, int t,
+                                            float4 (&v)[8]) {
     const int c = t & 7, r0 = t >> 3;
-    float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + 16 * i;
         v[i] = (row0 + r < rows_total) ? __ldg(reinterpret_cast<const float4 *>(src + map.off(row0 + r) + k0) + c)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+__device__ __forceinline__ void tile_store_k(const float4 (&v)[8], unsigned char *dst_hi, unsigned char *dst_lo, int t) {
+    const int c = t & 7, r0 = t >> 3;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = r0 + 16 * i;
@@ -113,6 +117,12 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ src, RowM
         *reinterpret_cast<float4 *>(dst_hi + off) = hi;
         *reinterpret_cast<float4 *>(dst_lo + off) = lo;
     }
+}
+__device__ __forceinline__ void produce_tile(const float *__restrict__ src, RowMap map, int row0, int rows_total, int k0,
+                                             unsigned char *dst_hi, unsigned char *dst_lo, int t) {
+    float4 v[8];
+    tile_load_k(src, map, row0, rows_total, k0, t, v);
+    tile_store_k(v, dst_hi, dst_lo, t);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *__restrict__ A, RowMap amap,
@@ -247,6 +257,159 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
 
 
 // =================================================================================================
+// K <= 128 specialisation (the unit-embedding GEMMs and the i2h projection at H = 128): the whole B operand of the
+// CTA's column block (<= 128 x 128, hi + lo = 128 KB) is split ONCE and stays resident in shared memory; the ring
+// stages carry only A (hi + lo, 32 KB each).  Every CTA owns one column block and walks the row blocks, and every
+// producer group keeps the next chunk's eight loads in flight while it splits the current one.
+constexpr int kStageBytesA = 2 * kTileBytes;
+constexpr int kMaxResChunks = 4;
+constexpr size_t kSmemBytesBRes = (size_t)kMaxResChunks * 2 * kTileBytes + (size_t)kStages * kStageBytesA + 1024 + 128;
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const float *__restrict__ A, RowMap amap,
+                                                                       const float *__restrict__ B, int ldb,
+                                                                       const float *__restrict__ bias, float *__restrict__ C,
+                                                                       RowMap cmap, int M, int N, int K, int relu) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *bres = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *tiles = bres + (size_t)kMaxResChunks * 2 * kTileBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytesA);
+    uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages, *acc_empty = bars + 2 * kStages + 2;
+    uint64_t *b_ready = bars + 2 * kStages + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
+    const int n_blk = blockIdx.x % n_blocks, m_first = blockIdx.x / n_blocks, m_step = gridDim.x / n_blocks;
+    const int n0 = n_blk * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        mbar_init(b_ready, kProducerThreads * kProducerGroups);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < kMmaWarp) {
+        // ===== PRODUCERS =====
+        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
+        for (int kc = g; kc < k_chunks; kc += kProducerGroups)            // the resident B block, once
+            produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
+                         bres + (size_t)kc * 2 * kTileBytes + kTileBytes, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(b_ready);
+        // A chunks: running chunk index c = tile_iter * k_chunks + kc; this group takes c == g (mod groups)
+        const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
+        const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
+        float4 v[8], vn[8];
+        uint32_t c = g;
+        if (c < total_chunks) tile_load_k(A, amap, (m_first + (int)(c / k_chunks) * m_step) * BM, M, (int)(c % k_chunks) * BK, t, v);
+        for (; c < total_chunks; c += kProducerGroups) {
+            const uint32_t cn = c + kProducerGroups;
+            if (cn < total_chunks)
+                tile_load_k(A, amap, (m_first + (int)(cn / k_chunks) * m_step) * BM, M, (int)(cn % k_chunks) * BK, t, vn);
+            const int stage = c % kStages;
+            mbar_wait(&empty[stage], ((c / kStages) & 1) ^ 1);
+            unsigned char *st = tiles + (size_t)stage * kStageBytesA;
+            tile_store_k(v, st, st + kTileBytes, t);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&full[stage]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = vn[i];
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA ISSUER =====
+        mbar_wait(b_ready, 0);
+        uint32_t c = 0;
+        int it = 0;
+        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
+            const int a = it & 1;
+            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + a * kAccCols;
+            for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+                const int stage = c % kStages;
+                mbar_wait(&full[stage], (c / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t abase = smem_u32(tiles + (size_t)stage * kStageBytesA);
+                    const uint32_t bbase = smem_u32(bres + (size_t)kc * 2 * kTileBytes);
+                    const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + kTileBytes);
+                    const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + kTileBytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t first = (kc | ks) != 0;
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, kIdesc, first);
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, kIdesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kc == k_chunks - 1) umma_commit(&acc_full[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== EPILOGUE =====
+        const int q = warp & 3;
+        int it = 0;
+        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
+            const int a = it & 1;
+            const int m0 = mb * BM;
+            mbar_wait(&acc_full[a], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            float *crow = C + cmap.off(row < M ? row : 0) + n0;
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kAccCols + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
+                        o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
+                        if (bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + cb + j));
+                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        }
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4 *>(crow + cb + j) = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[a]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// =================================================================================================
 // Weight-gradient GEMM:  dW[No, Ni] = dY[T, No]^T * X[T, Ni]   and   db[No] = column sums of dY.
 //
 // The contraction runs over the TOKEN dimension, so both operands are MN-major in memory (features contiguous).
@@ -267,19 +430,23 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
            (1ull << 46) | (1ull << 61);
 }
 
-// Loads tokens [t0, t0+32) x features [f0, f0+128) of a row-major [T, ld] matrix, splits hi/lo and stores MN-major atoms.
-// Returns (through colsum) this thread's running column sums for its 4 features.
-__device__ __forceinline__ void produce_tile_mn(const float *__restrict__ src, RowMap map, int t0, int T, int f0,
-                                                unsigned char *dst_hi, unsigned char *dst_lo, int t, float4 *colsum) {
+// MN-major operand chunk: tokens [t0, t0+32) x features [f0, f0+128) of a row-major [T, ld] matrix.  Load and
+// split/store halves are separate for register double buffering (see tile_load_k).  tile_store_mn optionally adds the
+// chunk to this thread's running column sums (4 features).
+__device__ __forceinline__ void tile_load_mn(const float *__restrict__ src, RowMap map, int t0, int T, int f0, int t,
+                                             float4 (&v)[8]) {
     const int l = t & 31, w = t >> 5;                  // lane -> 4 features, warp -> token (mod 4)
-    const int mi = l >> 3, c32 = (l & 7) >> 1, half = l & 1;     // 32-feature atom, 32-byte chunk, 16-byte half
-    float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int tok = w + 4 * i;
         v[i] = (t0 + tok < T) ? __ldg(reinterpret_cast<const float4 *>(src + map.off(t0 + tok) + f0) + l)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+__device__ __forceinline__ void tile_store_mn(const float4 (&v)[8], unsigned char *dst_hi, unsigned char *dst_lo, int t,
+                                              float4 *colsum) {
+    const int l = t & 31, w = t >> 5;
+    const int mi = l >> 3, c32 = (l & 7) >> 1, half = l & 1;     // 32-feature atom, 32-byte chunk, 16-byte half
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int tok = w + 4 * i;
@@ -313,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
     const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 2 * kProducerThreads); mbar_init(&empty[s], 1); }
         mbar_init(&acc_full[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -327,20 +494,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < kMmaWarp) {
-        // ===== PRODUCERS =====
+        // ===== PRODUCERS =====  work item i = (chunk i/2, operand i%2: 0 = dY, 1 = X); group g takes i == g (mod groups)
+        // and keeps the next item's eight loads in flight while it splits the current one.
         const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool want_b = part_b != nullptr && n0 == 0;
-        for (int j = g; j < my_chunks; j += kProducerGroups) {
+        const uint32_t total_items = 2u * (uint32_t)my_chunks;
+        auto load_item = [&](uint32_t i, float4 (&dst)[8]) {
+            const int t0 = (split + (int)(i >> 1) * nsplit) * BK;
+            if (i & 1) tile_load_mn(X, xmap, t0, T, n0, t, dst);
+            else tile_load_mn(dY, ymap, t0, T, m0, t, dst);
+        };
+        float4 v[8], vn[8];
+        uint32_t i = g;
+        if (i < total_items) load_item(i, v);
+        for (; i < total_items; i += kProducerGroups) {
+            if (i + kProducerGroups < total_items) load_item(i + kProducerGroups, vn);
+            const uint32_t j = i >> 1;
             const int stage = j % kStages;
-            const uint32_t phase = (j / kStages) & 1;
-            const int t0 = (split + j * nsplit) * BK;
-            mbar_wait(&empty[stage], phase ^ 1);
-            unsigned char *st = tiles + (size_t)stage * kStageBytes;
-            produce_tile_mn(dY, ymap, t0, T, m0, st, st + kTileBytes, t, want_b ? &cs : nullptr);
-            produce_tile_mn(X, xmap, t0, T, n0, st + 2 * kTileBytes, st + 3 * kTileBytes, t, nullptr);
+            mbar_wait(&empty[stage], ((j / kStages) & 1) ^ 1);
+            unsigned char *st = tiles + (size_t)stage * kStageBytes + ((i & 1) ? 2 * kTileBytes : 0);
+            tile_store_mn(v, st, st + kTileBytes, t, (want_b && !(i & 1)) ? &cs : nullptr);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full[stage]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = vn[q];
         }
         if (want_b) *reinterpret_cast<float4 *>(colsum_s + warp * 128 + lane * 4) = cs;
     } else if (warp == kMmaWarp) {
@@ -455,6 +633,20 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
         attr_set = true;
     }
     const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
+    const int n_blocks = N / BN, m_blocks = (int)((M + BM - 1) / BM);
+    if (K / BK <= kMaxResChunks && n_blocks <= dc_sm_count()) {          // resident-B specialisation
+        static bool attr_b = false;
+        if (!attr_b) {
+            DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_bres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBRes));
+            attr_b = true;
+        }
+        int per_col = dc_sm_count() / n_blocks;                          // CTAs per column block
+        if (per_col > m_blocks) per_col = m_blocks;
+        gemm_tf32x3_bres_kernel<<<per_col * n_blocks, kThreads, kSmemBytesBRes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
+                                                                                                       (int)M, N, K, relu);
+        DC_LAUNCH_OK();
+        return DC_OK;
+    }
     const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
     gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap, (int)M, N, K, relu);
     DC_LAUNCH_OK();
