@@ -125,10 +125,38 @@ __device__ __forceinline__ void produce_tile(const float *__restrict__ src, RowM
     tile_store_k(v, dst_hi, dst_lo, t);
 }
 
+// Epilogue store of 32 consecutive outputs of one row held by one thread.  `wide` = 256-bit stores (STG.256, sm_100):
+// every lane then writes whole 32-byte sectors; with 16-byte stores each sector is touched twice (ncu: 32 sectors per
+// request, half filled).
+__device__ __forceinline__ void store_row32(float *dst, const uint32_t (&r)[32], const float *bias, int relu, bool wide) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        float o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = __uint_as_float(r[j + q]);
+        if (bias) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + j)), b1 = __ldg(reinterpret_cast<const float4 *>(bias + j + 4));
+            o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+        }
+        if (relu) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = fmaxf(o[q], 0.f);
+        }
+        if (wide) {
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + j), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                         "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                         : "memory");
+        } else {
+            *reinterpret_cast<float4 *>(dst + j) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4 *>(dst + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *__restrict__ A, RowMap amap,
                                                                   const float *__restrict__ B, int ldb,
                                                                   const float *__restrict__ bias, float *__restrict__ C,
-                                                                  RowMap cmap, int M, int N, int K, int relu) {
+                                                                  RowMap cmap, int M, int N, int K, int relu, bool wide) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
@@ -228,20 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o;
-                        o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
-                        o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
-                        if (bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + cb + j));
-                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        }
-                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4 *>(crow + cb + j) = o;
-                    }
-                }
+                if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[a]);
@@ -268,7 +283,7 @@ constexpr size_t kSmemBytesBRes = (size_t)kMaxResChunks * 2 * kTileBytes + (size
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const float *__restrict__ A, RowMap amap,
                                                                        const float *__restrict__ B, int ldb,
                                                                        const float *__restrict__ bias, float *__restrict__ C,
-                                                                       RowMap cmap, int M, int N, int K, int relu) {
+                                                                       RowMap cmap, int M, int N, int K, int relu, bool wide) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *bres = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *tiles = bres + (size_t)kMaxResChunks * 2 * kTileBytes;
@@ -382,20 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o;
-                        o.x = __uint_as_float(r[j]); o.y = __uint_as_float(r[j + 1]);
-                        o.z = __uint_as_float(r[j + 2]); o.w = __uint_as_float(r[j + 3]);
-                        if (bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias + n0 + cb + j));
-                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        }
-                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                        *reinterpret_cast<float4 *>(crow + cb + j) = o;
-                    }
-                }
+                if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[a]);
@@ -571,9 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4 *>(prow + cb + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            store_row32(prow + cb, r, nullptr, 0, true);                      // workspace rows are 512-byte aligned
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -632,6 +632,9 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
         DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
         attr_set = true;
     }
+    // 256-bit epilogue stores need 32-byte aligned rows
+    const bool wide = ((uintptr_t)C & 31) == 0 && ldc % 8 == 0 && (cmap.rpb == 0 || cmap.bs % 8 == 0) &&
+                      (!bias || ((uintptr_t)bias & 31) == 0);
     const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
     const int n_blocks = N / BN, m_blocks = (int)((M + BM - 1) / BM);
     if (K / BK <= kMaxResChunks && n_blocks <= dc_sm_count()) {          // resident-B specialisation
@@ -643,12 +646,12 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
         int per_col = dc_sm_count() / n_blocks;                          // CTAs per column block
         if (per_col > m_blocks) per_col = m_blocks;
         gemm_tf32x3_bres_kernel<<<per_col * n_blocks, kThreads, kSmemBytesBRes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
-                                                                                                       (int)M, N, K, relu);
+                                                                                                       (int)M, N, K, relu, wide);
         DC_LAUNCH_OK();
         return DC_OK;
     }
     const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
-    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap, (int)M, N, K, relu);
+    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap, (int)M, N, K, relu, wide);
     DC_LAUNCH_OK();
     return DC_OK;
 }
