@@ -144,18 +144,41 @@ def cpu_reference_steps_per_sec(cfg, budget_s=20.0, threads=None):
 
 
 def run_reference_arm(args, cfg):
-    """``--impl reference``: the reference's CPU train() (oracle port) on all host cores; rank 0 only."""
+    """``--impl reference``: the reference's CPU ``train()`` (oracle port: the reference is pure Python + torch CPU and
+    cannot travel to the GPU box) on the host cores, same config/metric.  Each step is one train() on a bounded sample
+    (``b`` of the config's ``batch`` sequences, full seq_len); steps/s is scaled by b/batch.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps_per_s_samples = []
-    cores, sample = usable_cores(), ""
-    per = max(3.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=per)
-        if i >= args.warmup:
-            steps_per_s_samples.append(v)
-    value = sum(steps_per_s_samples) / len(steps_per_s_samples)
+    import torch
+    from oracle import ref_optimizer as RO
+    from oracle.ref_policy import RefPolicy
+    from dotaclient_b200.synthetic import make_rollout
+    cores = min(usable_cores(), 64)
+    torch.set_num_threads(cores)
+    S, H, cell, B = cfg["seq_len"], cfg["hidden"], cfg["cell"], cfg["batch"]
+    torch.manual_seed(7)
+    opt = RO.RefOptimizer(RefPolicy(H, cell), seq_len=S)
+    seqs = opt.experiences_from_rollout(make_rollout(S, 7))
+    b = 1
+    while True:                                            # grow the sample until one step takes >= 1 s (cap 32 sequences)
+        t0 = time.perf_counter()
+        opt.train(seqs)
+        if time.perf_counter() - t0 >= 1.0 or b >= B or b >= 32:
+            break
+        for i in range(b):
+            seqs.extend(opt.experiences_from_rollout(make_rollout(S, 7 + b + i)))
+        b *= 2
+    b = len(seqs)
+    for _ in range(args.warmup):
+        opt.train(seqs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        opt.train(seqs)
+    el = time.perf_counter() - t0
+    value = args.steps / el * b / B
+    sample = "oracle port of optimizer.py:581-689, batch %d x seq %d (hidden %d, %s), %d steps in %.1f s on %d threads; " \
+             "scaled x%d/%d to batch %d" % (b, S, H, cell, args.steps, el, cores, b, B, B)
     line = {
         "impl": "reference", "metric": "optimizer_steps_per_sec", "value": value, "unit": "steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
@@ -163,7 +186,7 @@ def run_reference_arm(args, cfg):
         "config": workload_config(cfg, args.gpus, "cpu"),
         "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU data-parallel ranks of the reference run the same per-rank batch concurrently; one host, so N>1 is not faster",
+        "note": "one host: N reference ranks would share these cores, so the per-rank-batch rate does not grow with N",
     }
     print(json.dumps(line))
 

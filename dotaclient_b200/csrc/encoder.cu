@@ -31,12 +31,13 @@ __global__ void __launch_bounds__(kThreadsE) unit_basic_fwd_kernel(const float *
                                                                    float *__restrict__ basic, int64_t R) {
     __shared__ float s_u[kWarps][32][kIn];                        // 32 rows of raw features per warp per iteration
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float w[4][kIn], b[4];
+    // weights as channel PAIRS for the packed fp32x2 FMA (FFMA2): w2[p][k] = (W_b[4l+2p][k], W_b[4l+2p+1][k])
+    float2 w2[2][kIn], b2[2];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        b[c] = b_b[lane * 4 + c];
+    for (int p = 0; p < 2; ++p) {
+        b2[p] = make_float2(b_b[lane * 4 + 2 * p], b_b[lane * 4 + 2 * p + 1]);
 #pragma unroll
-        for (int k = 0; k < kIn; ++k) w[c][k] = w_b[(lane * 4 + c) * kIn + k];
+        for (int k = 0; k < kIn; ++k) w2[p][k] = make_float2(w_b[(lane * 4 + 2 * p) * kIn + k], w_b[(lane * 4 + 2 * p + 1) * kIn + k]);
     }
     const int64_t rows_per_iter = (int64_t)gridDim.x * kWarps * 32;
     for (int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * 32; base < R; base += rows_per_iter) {
@@ -46,15 +47,16 @@ __global__ void __launch_bounds__(kThreadsE) unit_basic_fwd_kernel(const float *
         for (int i = lane; i < nrows * kIn; i += 32) su[i] = units[base * kIn + i];
         __syncwarp();
         for (int r = 0; r < nrows; ++r) {
-            float acc[4] = {b[0], b[1], b[2], b[3]};
+            float2 a0 = b2[0], a1 = b2[1];
 #pragma unroll
             for (int k = 0; k < kIn; ++k) {
                 const float u = s_u[warp][r][k];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c] = fmaf(u, w[c][k], acc[c]);
+                const float2 uu = make_float2(u, u);
+                a0 = __ffma2_rn(uu, w2[0][k], a0);
+                a1 = __ffma2_rn(uu, w2[1][k], a1);
             }
             *reinterpret_cast<float4 *>(basic + (base + r) * kC + lane * 4) =
-                make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+                make_float4(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f), fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
         }
         __syncwarp();
     }
@@ -69,11 +71,14 @@ __global__ void __launch_bounds__(kThreadsE, 2) unit_basic_bwd_kernel(const floa
     __shared__ float s_u[kWarps][32][kIn];
     __shared__ float s_red[kC][kIn + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float acc[4][kIn + 1];
+    float2 acc2[4][kIn / 2];       // (dW[c][2kk], dW[c][2kk+1]) pairs for FFMA2
+    float accb[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 4; ++c) {
+        accb[c] = 0.f;
 #pragma unroll
-        for (int k = 0; k <= kIn; ++k) acc[c][k] = 0.f;
+        for (int kk = 0; kk < kIn / 2; ++kk) acc2[c][kk] = make_float2(0.f, 0.f);
+    }
     const int64_t rows_per_iter = (int64_t)gridDim.x * kWarps * 32;
     for (int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * 32; base < R; base += rows_per_iter) {
         const int nrows = (int)min((int64_t)32, R - base);
@@ -94,13 +99,13 @@ __global__ void __launch_bounds__(kThreadsE, 2) unit_basic_bwd_kernel(const floa
                 const float g[4] = {y4[j].x > 0.f ? g4[j].x : 0.f, y4[j].y > 0.f ? g4[j].y : 0.f,
                                     y4[j].z > 0.f ? g4[j].z : 0.f, y4[j].w > 0.f ? g4[j].w : 0.f};
 #pragma unroll
-                for (int k = 0; k < kIn; ++k) {
-                    const float u = s_u[warp][r0 + j][k];
+                for (int kk = 0; kk < kIn / 2; ++kk) {
+                    const float2 u2 = *reinterpret_cast<const float2 *>(&s_u[warp][r0 + j][2 * kk]);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[c][k] = fmaf(g[c], u, acc[c][k]);
+                    for (int c = 0; c < 4; ++c) acc2[c][kk] = __ffma2_rn(make_float2(g[c], g[c]), u2, acc2[c][kk]);
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[c][kIn] += g[c];
+                for (int c = 0; c < 4; ++c) accb[c] += g[c];
             }
         }
         __syncwarp();
@@ -113,7 +118,8 @@ __global__ void __launch_bounds__(kThreadsE, 2) unit_basic_bwd_kernel(const floa
 #pragma unroll
                 for (int k = 0; k <= kIn; ++k) {
                     float *dst = &s_red[lane * 4 + c][k];
-                    *dst = (w == 0 ? 0.f : *dst) + acc[c][k];
+                    const float mine = k == kIn ? accb[c] : ((k & 1) ? acc2[c][k >> 1].y : acc2[c][k >> 1].x);
+                    *dst = (w == 0 ? 0.f : *dst) + mine;
                 }
         }
         __syncthreads();

@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
     const int tiles_total = m_blocks * n_blocks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {   // TMEM allocation: one full warp; the address lands in shared memory
@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
                 produce_tile(A, amap, m0, M, kc * BK, st, st + kTileBytes, t);
                 produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-                mbar_arrive(&full[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
             }
         }
     } else if (warp == kMmaWarp) {
@@ -259,7 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
                 if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[a]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -298,9 +300,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
     const int n0 = n_blk * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
-        mbar_init(b_ready, kProducerThreads * kProducerGroups);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        mbar_init(b_ready, kProducerThreads * kProducerGroups / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -319,7 +321,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
             produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
                          bres + (size_t)kc * 2 * kTileBytes + kTileBytes, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(b_ready);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_ready);
         // A chunks: running chunk index c = tile_iter * k_chunks + kc; this group takes c == g (mod groups)
         const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
         const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
             unsigned char *st = tiles + (size_t)stage * kStageBytesA;
             tile_store_k(v, st, st + kTileBytes, t);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full[stage]);
+            __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = vn[i];
         }
@@ -400,7 +404,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
                 if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[a]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
     const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 2 * kProducerThreads); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 2 * kProducerThreads / 32); mbar_init(&empty[s], 1); }
         mbar_init(&acc_full[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -518,7 +523,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
             unsigned char *st = tiles + (size_t)stage * kStageBytes + ((i & 1) ? 2 * kTileBytes : 0);
             tile_store_mn(v, st, st + kTileBytes, t, (want_b && !(i & 1)) ? &cs : nullptr);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&full[stage]);
+            __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = vn[q];
         }

@@ -8,7 +8,7 @@ read their group's slice of the unit-embedding tensor in place), no dense zeros+
 import torch
 
 from . import _lib
-from .ops import PROFILE, _f32c, _need_cuda, gemm_wgrad_supported
+from .ops import PROFILE, _f32c, _need_cuda, gemm_wgrad_supported, wait_h2d
 
 UNITS = (1, 5, 16, 16, 1, 1)              # allied/enemy heroes, allied/enemy non-heroes, allied/enemy towers
 OFFSETS = (0, 1, 6, 22, 38, 39)
@@ -71,6 +71,7 @@ class UnitEncoder(torch.autograd.Function):
         for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
             R = N * n_u
             basic = torch.empty((R, C), dtype=torch.float32, device=dev)
+            wait_h2d(units[g])                       # this group's observations may still be in flight over PCIe
             with PROFILE.span("unit_basic_fwd", 1):
                 _lib.check(lib.dc_unit_basic_fwd(units[g].data_ptr(), w_b.data_ptr(), b_b.data_ptr(), basic.data_ptr(), R, st),
                            "dc_unit_basic_fwd")

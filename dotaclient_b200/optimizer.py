@@ -233,9 +233,34 @@ class ExperienceBatch:
         return sum(v.numel() * v.element_size() for _, _, v in self.tensors())
 
     def to(self, device, non_blocking=True):
+        """Host -> device.  From pinned memory the copies are issued on a side stream in the order the step consumes
+        them (env, states, unit groups, then the loss inputs) and every tensor gets an event: ``train`` makes the
+        compute stream wait per tensor right before first use, so the PCIe transfer of unit group g+1 overlaps the
+        encoder kernels of group g and the loss inputs arrive during forward/backward."""
         out = ExperienceBatch({}, {}, {}, None, None, None, None, None)
-        for holder, k, v in self.tensors():
-            moved = v.to(device, non_blocking=non_blocking)
+        overlap = non_blocking and self.advantages.is_pinned()
+        compute = torch.cuda.current_stream(device)
+        side = _copy_stream(device) if overlap else None
+        if overlap:
+            side.wait_stream(compute)
+        def priority(item):                      # copy order == order of first use in the step
+            holder, k, _ = item
+            if holder is self.observations:
+                return 0 if k == 'env' else 3 + Policy.INPUT_KEYS.index(k)
+            if not isinstance(holder, dict) and k in ('h0', 'c0'):
+                return 1
+            return 100
+        items = sorted(self.tensors(), key=priority)
+        for holder, k, v in items:
+            if overlap:
+                with torch.cuda.stream(side):
+                    moved = v.to(device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                moved.record_stream(compute)
+                ops.H2D_EVENTS[moved.data_ptr()] = ev
+            else:
+                moved = v.to(device, non_blocking=non_blocking)
             if isinstance(holder, dict):
                 target = out.observations if holder is self.observations else out.masks if holder is self.masks else out.actions
                 target[k] = moved
@@ -271,6 +296,16 @@ class ExperienceBatch:
         else:
             h0, c0 = torch.cat([e.hidden.to(device) for e in experiences], dim=1), None      # :591
         return ExperienceBatch(obs, masks, actions, old, adv, ret, h0.detach(), None if c0 is None else c0.detach())
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
 
 
 def all_gather(t):                                                        # :193-196 (unused by the reference too)
@@ -472,7 +507,10 @@ class DotaOptimizer:
         ddp = self.policy if isinstance(self.policy, DistributedDataParallelSparseParamCPU) else None
         if ddp is not None:
             ddp.auto_reduce = False        # the count-divide is fused into the finish kernel below
+        ops.wait_h2d(batch.observations['env'], batch.h0, batch.c0)
         logits, values, _ = self.policy.forward_time_major(batch.observations, hidden)   # :619
+        ops.wait_h2d(batch.old_logp, batch.advantages, batch.returns, *batch.masks.values(), *batch.actions.values(),
+                     *batch.observations.values())
         out, n_actions, dlogits, dvalue = ops.ppo_loss_fwd_bwd(
             [logits[k] for k in keys], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
             batch.old_logp, batch.advantages, batch.returns, values, self.e_clip, self.entropy_coef, self.vf_coef)
