@@ -46,6 +46,9 @@ struct HeadPtrs {
     const uint8_t *masks[kHeads];
     const uint8_t *actions[kHeads];
     float *dlogits[kHeads];
+    long long ld_l[kHeads];     // row pitch (floats) of logits[h]; == n_h when contiguous.  A pitch of 128 lets the four
+    long long ld_d[kHeads];     // small heads + value live as column ranges of ONE packed [N,128] GEMM output / gradient
+    long long ld_v, ld_dv;      // pitches of value / dvalue
 };
 
 // Workspace layout (DC_PPO_WORKSPACE_BYTES, zeroed per call)
@@ -62,8 +65,13 @@ static_assert(sizeof(Workspace) <= DC_PPO_WORKSPACE_BYTES, "workspace too small"
 
 // Cooperative copy of `count` rows of N floats (contiguous in global) into smem rows of pitch P.
 template <int N, int P>
-__device__ __forceinline__ void stage_rows_f32(float *dst, const float *__restrict__ src, int count) {
+__device__ __forceinline__ void stage_rows_f32(float *dst, const float *__restrict__ base, long long ld, int64_t t0, int count) {
     const int total = count * N;
+    if (ld != N) {                                   // strided rows (column range of a wider matrix)
+        for (int idx = threadIdx.x; idx < total; idx += kTile) dst[(idx / N) * P + (idx % N)] = base[(t0 + idx / N) * ld + (idx % N)];
+        return;
+    }
+    const float *src = base + t0 * N;
     if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
         const int nvec = total >> 2;
         for (int i = threadIdx.x; i < nvec; i += kTile) {
@@ -82,8 +90,13 @@ __device__ __forceinline__ void stage_rows_f32(float *dst, const float *__restri
 }
 
 template <int N, int P>
-__device__ __forceinline__ void unstage_rows_f32(float *__restrict__ dst, const float *src, int count) {
+__device__ __forceinline__ void unstage_rows_f32(float *__restrict__ base, long long ld, int64_t t0, const float *src, int count) {
     const int total = count * N;
+    if (ld != N) {
+        for (int idx = threadIdx.x; idx < total; idx += kTile) base[(t0 + idx / N) * ld + (idx % N)] = src[(idx / N) * P + (idx % N)];
+        return;
+    }
+    float *dst = base + t0 * N;
     if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         const int nvec = total >> 2;
         for (int i = threadIdx.x; i < nvec; i += kTile) {
@@ -270,12 +283,12 @@ __global__ void __launch_bounds__(kTile) ppo_loss_kernel(HeadPtrs hp, const floa
 
     const int64_t t0 = (int64_t)blockIdx.x * kTile;
     const int count = (int)min((int64_t)kTile, N - t0);
-    stage_rows_f32<4, 5>(s_logits + logit_off(0), hp.logits[0] + t0 * 4, count);
-    stage_rows_f32<9, 9>(s_logits + logit_off(1), hp.logits[1] + t0 * 9, count);
-    stage_rows_f32<9, 9>(s_logits + logit_off(2), hp.logits[2] + t0 * 9, count);
-    stage_rows_f32<40, 41>(s_logits + logit_off(3), hp.logits[3] + t0 * 40, count);
-    stage_rows_f32<3, 3>(s_logits + logit_off(4), hp.logits[4] + t0 * 3, count);
-    if (!kSelectOnly) stage_rows_f32<5, 5>(s_old, old_logp + t0 * 5, count);
+    stage_rows_f32<4, 5>(s_logits + logit_off(0), hp.logits[0], hp.ld_l[0], t0, count);
+    stage_rows_f32<9, 9>(s_logits + logit_off(1), hp.logits[1], hp.ld_l[1], t0, count);
+    stage_rows_f32<9, 9>(s_logits + logit_off(2), hp.logits[2], hp.ld_l[2], t0, count);
+    stage_rows_f32<40, 41>(s_logits + logit_off(3), hp.logits[3], hp.ld_l[3], t0, count);
+    stage_rows_f32<3, 3>(s_logits + logit_off(4), hp.logits[4], hp.ld_l[4], t0, count);
+    if (!kSelectOnly) stage_rows_f32<5, 5>(s_old, old_logp, 5, t0, count);
 #pragma unroll
     for (int h = 0; h < kHeads; ++h) {
         stage_bytes(s_mask + byte_off(h), hp.masks[h] + t0 * head_n(h), count * head_n(h));
@@ -309,19 +322,19 @@ __global__ void __launch_bounds__(kTile) ppo_loss_kernel(HeadPtrs hp, const floa
 #pragma unroll
             for (int h = 0; h < kHeads; ++h) logp_out[(t0 + t) * 5 + h] = lp_sel[h];
         } else {
-            const float v = value[t0 + t], r = ret[t0 + t];
+            const float v = value[(t0 + t) * hp.ld_v], r = ret[t0 + t];
             const float d = r - v;
             vl = d * d;                                                     // optimizer.py:660
-            dvalue[t0 + t] = vf_coef > 0.f ? vf_coef * (v - r) / (float)N : 0.f;
+            dvalue[(t0 + t) * hp.ld_dv] = vf_coef > 0.f ? vf_coef * (v - r) / (float)N : 0.f;
         }
     }
     if (kSelectOnly) return;
     __syncthreads();
-    unstage_rows_f32<4, 5>(hp.dlogits[0] + t0 * 4, s_logits + logit_off(0), count);
-    unstage_rows_f32<9, 9>(hp.dlogits[1] + t0 * 9, s_logits + logit_off(1), count);
-    unstage_rows_f32<9, 9>(hp.dlogits[2] + t0 * 9, s_logits + logit_off(2), count);
-    unstage_rows_f32<40, 41>(hp.dlogits[3] + t0 * 40, s_logits + logit_off(3), count);
-    unstage_rows_f32<3, 3>(hp.dlogits[4] + t0 * 3, s_logits + logit_off(4), count);
+    unstage_rows_f32<4, 5>(hp.dlogits[0], hp.ld_d[0], t0, s_logits + logit_off(0), count);
+    unstage_rows_f32<9, 9>(hp.dlogits[1], hp.ld_d[1], t0, s_logits + logit_off(1), count);
+    unstage_rows_f32<9, 9>(hp.dlogits[2], hp.ld_d[2], t0, s_logits + logit_off(2), count);
+    unstage_rows_f32<40, 41>(hp.dlogits[3], hp.ld_d[3], t0, s_logits + logit_off(3), count);
+    unstage_rows_f32<3, 3>(hp.dlogits[4], hp.ld_d[4], t0, s_logits + logit_off(4), count);
 
     float sums[2 * kHeads + 1];
 #pragma unroll
@@ -374,20 +387,26 @@ int check_heads(const float *const logits[], const uint8_t *const masks[], const
 
 }  // namespace
 
-extern "C" int dc_ppo_loss_fwd_bwd(const float *const logits[DC_NUM_HEADS], const uint8_t *const masks[DC_NUM_HEADS],
-                                   const uint8_t *const actions[DC_NUM_HEADS], const float *old_logp,
-                                   const float *adv_raw, const float *ret, const float *value, int64_t N,
-                                   float e_clip, float entropy_coef, float vf_coef,
-                                   float *const dlogits[DC_NUM_HEADS], float *dvalue, float *out,
-                                   int32_t *n_actions, void *workspace, dc_stream_t stream) {
+extern "C" int dc_ppo_loss_fwd_bwd_strided(const float *const logits[DC_NUM_HEADS], const int64_t ld_logits[DC_NUM_HEADS],
+                                           const uint8_t *const masks[DC_NUM_HEADS],
+                                           const uint8_t *const actions[DC_NUM_HEADS], const float *old_logp,
+                                           const float *adv_raw, const float *ret, const float *value, int64_t ld_value,
+                                           int64_t N, float e_clip, float entropy_coef, float vf_coef,
+                                           float *const dlogits[DC_NUM_HEADS], const int64_t ld_dlogits[DC_NUM_HEADS],
+                                           float *dvalue, int64_t ld_dvalue, float *out, int32_t *n_actions, void *workspace,
+                                           dc_stream_t stream) {
     DC_REQUIRE(N > 0, DC_EINVAL, "dc_ppo_loss_fwd_bwd: N=%lld", (long long)N);
     DC_REQUIRE(check_heads(logits, masks, actions) && old_logp && adv_raw && ret && value && dvalue && out &&
-                   n_actions && workspace, DC_EINVAL, "dc_ppo_loss_fwd_bwd: null pointer");
+                   n_actions && workspace && ld_logits && ld_dlogits, DC_EINVAL, "dc_ppo_loss_fwd_bwd: null pointer");
     HeadPtrs hp;
     for (int h = 0; h < kHeads; ++h) {
         DC_REQUIRE(dlogits[h], DC_EINVAL, "dc_ppo_loss_fwd_bwd: null dlogits[%d]", h);
+        DC_REQUIRE(ld_logits[h] >= head_n(h) && ld_dlogits[h] >= head_n(h), DC_EINVAL, "dc_ppo_loss_fwd_bwd: row pitch of head %d", h);
         hp.logits[h] = logits[h]; hp.masks[h] = masks[h]; hp.actions[h] = actions[h]; hp.dlogits[h] = dlogits[h];
+        hp.ld_l[h] = ld_logits[h]; hp.ld_d[h] = ld_dlogits[h];
     }
+    DC_REQUIRE(ld_value >= 1 && ld_dvalue >= 1, DC_EINVAL, "dc_ppo_loss_fwd_bwd: value pitch");
+    hp.ld_v = ld_value; hp.ld_dv = ld_dvalue;
     cudaStream_t st = dc_cu_stream(stream);
     Workspace *ws = reinterpret_cast<Workspace *>(workspace);
     DC_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), st));
@@ -406,6 +425,17 @@ extern "C" int dc_ppo_loss_fwd_bwd(const float *const logits[DC_NUM_HEADS], cons
     return DC_OK;
 }
 
+extern "C" int dc_ppo_loss_fwd_bwd(const float *const logits[DC_NUM_HEADS], const uint8_t *const masks[DC_NUM_HEADS],
+                                   const uint8_t *const actions[DC_NUM_HEADS], const float *old_logp,
+                                   const float *adv_raw, const float *ret, const float *value, int64_t N,
+                                   float e_clip, float entropy_coef, float vf_coef,
+                                   float *const dlogits[DC_NUM_HEADS], float *dvalue, float *out,
+                                   int32_t *n_actions, void *workspace, dc_stream_t stream) {
+    const int64_t ld[DC_NUM_HEADS] = {4, 9, 9, 40, 3};
+    return dc_ppo_loss_fwd_bwd_strided(logits, ld, masks, actions, old_logp, adv_raw, ret, value, 1, N, e_clip, entropy_coef,
+                                       vf_coef, dlogits, ld, dvalue, 1, out, n_actions, workspace, stream);
+}
+
 extern "C" int dc_selected_logp(const float *const logits[DC_NUM_HEADS], const uint8_t *const masks[DC_NUM_HEADS],
                                 const uint8_t *const actions[DC_NUM_HEADS], int64_t N, float *logp_out,
                                 dc_stream_t stream) {
@@ -414,7 +444,9 @@ extern "C" int dc_selected_logp(const float *const logits[DC_NUM_HEADS], const u
     HeadPtrs hp;
     for (int h = 0; h < kHeads; ++h) {
         hp.logits[h] = logits[h]; hp.masks[h] = masks[h]; hp.actions[h] = actions[h]; hp.dlogits[h] = nullptr;
+        hp.ld_l[h] = head_n(h); hp.ld_d[h] = head_n(h);
     }
+    hp.ld_v = 1; hp.ld_dv = 1;
     static bool attr_set = false;
     if (!attr_set) {
         DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));

@@ -462,3 +462,45 @@ def gemm_wgrad_tf32x3(dy, x, want_bias=True, dw_out=None, db_out=None, accumulat
                                             1 if accumulate else 0, ws.data_ptr(), _lib.stream_ptr()),
                    "dc_gemm_wgrad_tf32x3")
     return dw_out, (db_out if want_bias else None)
+
+
+# --------------------------------------------------------------------------------------------- packed small heads
+PACK_COLS = {"enum": (0, 4), "x": (4, 13), "y": (13, 22), "ability": (22, 25), "value": (25, 26)}   # columns of the packed GEMM
+PACK_WIDTH = 128
+
+
+def ppo_loss_packed(packed, logits_tu, masks, actions, old_logp, adv_raw, ret, e_clip, entropy_coef, vf_coef):
+    """Fused PPO loss where the four small heads and the value head are column ranges of ONE packed ``[N,128]``
+    tensor-core GEMM output (``PACK_COLS``) and the target-unit logits are a separate ``[N,40]`` tensor.
+
+    Returns (out[16], n_actions[5], d_packed [N,128], d_logits_tu [N,40]): the gradients go straight back into the two
+    producers, so no slice/cat kernels run and the five tiny K=131072 weight-gradient GEMMs become one tcgen05 wgrad.
+    """
+    _need_cuda(packed, logits_tu)
+    p2 = _f32c(packed.detach()).reshape(-1, PACK_WIDTH)
+    N = p2.shape[0]
+    tu = _f32c(logits_tu.detach()).reshape(N, 40)
+    masks = [_u8(m) for m in masks]
+    actions = [_u8(a) for a in actions]
+    old_logp, adv_raw, ret = _f32c(old_logp), _f32c(adv_raw), _f32c(ret)
+    dev = p2.device
+    d_packed = torch.zeros_like(p2)            # the 102 padding columns must carry a zero gradient
+    d_tu = torch.empty_like(tu)
+    out = torch.empty(_lib.LOSS_SLOTS, dtype=torch.float32, device=dev)
+    n_actions = torch.empty(5, dtype=torch.int32, device=dev)
+    ws = torch.empty(_lib.PPO_WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+
+    def col(t, key):
+        return t.data_ptr() + 4 * PACK_COLS[key][0]
+    c = _lib._c
+    lptr = _lib._ptr5(col(p2, "enum"), col(p2, "x"), col(p2, "y"), tu.data_ptr(), col(p2, "ability"))
+    dptr = _lib._ptr5(col(d_packed, "enum"), col(d_packed, "x"), col(d_packed, "y"), d_tu.data_ptr(), col(d_packed, "ability"))
+    ld = (c.c_int64 * 5)(PACK_WIDTH, PACK_WIDTH, PACK_WIDTH, 40, PACK_WIDTH)
+    lib = _lib.load()
+    with PROFILE.span("ppo_loss", 2):
+        _lib.check(lib.dc_ppo_loss_fwd_bwd_strided(lptr, ld, _lib.ptr5(masks), _lib.ptr5(actions), old_logp.data_ptr(),
+                                                   adv_raw.data_ptr(), ret.data_ptr(), col(p2, "value"), PACK_WIDTH, N,
+                                                   float(e_clip), float(entropy_coef), float(vf_coef), dptr, ld,
+                                                   col(d_packed, "value"), PACK_WIDTH, out.data_ptr(), n_actions.data_ptr(),
+                                                   ws.data_ptr(), _lib.stream_ptr()), "dc_ppo_loss_fwd_bwd_strided")
+    return out, n_actions, d_packed.view_as(packed), d_tu.view_as(logits_tu)

@@ -511,12 +511,20 @@ class DotaOptimizer:
         logits, values, _ = self.policy.forward_time_major(batch.observations, hidden)   # :619
         ops.wait_h2d(batch.old_logp, batch.advantages, batch.returns, *batch.masks.values(), *batch.actions.values(),
                      *batch.observations.values())
-        out, n_actions, dlogits, dvalue = ops.ppo_loss_fwd_bwd(
-            [logits[k] for k in keys], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
-            batch.old_logp, batch.advantages, batch.returns, values, self.e_clip, self.entropy_coef, self.vf_coef)
-        self._n_actions[:5].copy_(n_actions)
-        torch.autograd.backward([logits[k] for k in keys] + [values],
-                                [g.view_as(logits[k]) for g, k in zip(dlogits, keys)] + [dvalue.view_as(values)])  # :672
+        packed = getattr(self.policy_base, "_packed_heads", None)
+        if packed is not None:          # small heads + value are column ranges of one packed GEMM output
+            out, n_actions, d_packed, d_tu = ops.ppo_loss_packed(
+                packed, logits['target_unit'], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
+                batch.old_logp, batch.advantages, batch.returns, self.e_clip, self.entropy_coef, self.vf_coef)
+            self._n_actions[:5].copy_(n_actions)
+            torch.autograd.backward([packed, logits['target_unit']], [d_packed, d_tu])                     # :672
+        else:
+            out, n_actions, dlogits, dvalue = ops.ppo_loss_fwd_bwd(
+                [logits[k] for k in keys], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
+                batch.old_logp, batch.advantages, batch.returns, values, self.e_clip, self.entropy_coef, self.vf_coef)
+            self._n_actions[:5].copy_(n_actions)
+            torch.autograd.backward([logits[k] for k in keys] + [values],
+                                    [g.view_as(logits[k]) for g, k in zip(dlogits, keys)] + [dvalue.view_as(values)])  # :672
         # distributed.py:29-57 -> flags + ONE all-reduce; divide fused into the finish kernel
         ops.grad_flags(self.flat.grad_full, self.flat.total, self.flat.seg_head, self._n_actions)
         if ddp is not None:

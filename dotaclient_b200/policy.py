@@ -151,6 +151,23 @@ class Policy(nn.Module):
     def _heads(self, y, unit_embedding):
         """Action heads + value (``policy.py:144-155``).  Creation order as the reference's."""
         attention = ops.linear(y, self.affine_unit_attention.weight, self.affine_unit_attention.bias).unsqueeze(-2)
+        H = self.hidden_size
+        if ops._TC_ENABLED and y.is_cuda and ops.gemm_tf32x3_supported(y.numel() // H, ops.PACK_WIDTH, H):
+            # the four small heads + the value head as ONE [*, 128] tensor-core GEMM (26 real rows, zero padding):
+            # their logits are column ranges of its output (ops.PACK_COLS)
+            pad = y.new_zeros(ops.PACK_WIDTH - 26, H)
+            w_pack = torch.cat([self.affine_head_enum.weight, self.affine_move_x.weight, self.affine_move_y.weight,
+                                self.affine_head_ability.weight, self.affine_value.weight, pad], dim=0)
+            b_pack = torch.cat([self.affine_head_enum.bias, self.affine_move_x.bias, self.affine_move_y.bias,
+                                self.affine_head_ability.bias, self.affine_value.bias, pad[:, 0]], dim=0)
+            packed = ops.linear(y, w_pack, b_pack)
+            self._packed_heads = packed                      # DotaOptimizer.train feeds gradients to it directly
+            cols = ops.PACK_COLS
+            head_enum, move_x, move_y, ability, value = (packed[..., cols[k][0]:cols[k][1]]
+                                                         for k in ("enum", "x", "y", "ability", "value"))
+            target_unit = encoder_ops.target_unit(attention.squeeze(-2), unit_embedding)
+            return {'enum': head_enum, 'x': move_x, 'y': move_y, 'target_unit': target_unit, 'ability': ability}, value
+        self._packed_heads = None
         move_x = self.affine_move_x(y)
         move_y = self.affine_move_y(y)
         head_enum = self.affine_head_enum(y)

@@ -163,6 +163,17 @@ int dc_ppo_loss_fwd_bwd(const float *const logits[DC_NUM_HEADS],
                         float *const dlogits[DC_NUM_HEADS], float *dvalue, float *out,
                         int32_t *n_actions, void *workspace, dc_stream_t stream);
 
+/* Same, with row pitches (floats) for logits[h], dlogits[h], value and dvalue: a pitch of 128 lets the four small heads
+ * and the value head be column ranges of ONE packed [N,128] tensor-core GEMM output and of its gradient. */
+int dc_ppo_loss_fwd_bwd_strided(const float *const logits[DC_NUM_HEADS], const int64_t ld_logits[DC_NUM_HEADS],
+                                const uint8_t *const masks[DC_NUM_HEADS],
+                                const uint8_t *const actions[DC_NUM_HEADS], const float *old_logp,
+                                const float *adv_raw, const float *ret, const float *value, int64_t ld_value,
+                                int64_t N, float e_clip, float entropy_coef, float vf_coef,
+                                float *const dlogits[DC_NUM_HEADS], const int64_t ld_dlogits[DC_NUM_HEADS],
+                                float *dvalue, int64_t ld_dvalue, float *out, int32_t *n_actions,
+                                void *workspace, dc_stream_t stream);
+
 /* Log-prob of the taken action per head, [N,5] dense (0 where the head took no action):
  * the no-grad half of experiences_from_rollout (optimizer.py:387-390). */
 int dc_selected_logp(const float *const logits[DC_NUM_HEADS],
