@@ -427,7 +427,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N=1 only
         log("timing the CPU baseline (oracle port)")
         v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=20.0)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}

@@ -35,6 +35,7 @@ SIGNATURES = {
     "dc_unit_basic_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dc_unit_max_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
     "dc_unit_max_bwd": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "dc_unit_grad_assemble": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "dc_target_unit_fwd": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "dc_target_unit_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "dc_ppo_loss_fwd_bwd": (_i32, [_ptr5, _ptr5, _ptr5, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _ptr5, _vp, _vp,

@@ -128,6 +128,120 @@ __global__ void __launch_bounds__(kThreadsE, 2) unit_basic_bwd_kernel(const floa
         partial[(size_t)blockIdx.x * kC * (kIn + 1) + i] = (&s_red[0][0])[i];
 }
 
+// TMA-staged variant: the three input streams (d_basic, basic, units) are contiguous row ranges, so a whole 64-row tile
+// is three 1-D bulk copies (cp.async.bulk + mbarrier complete_tx) into a 3-stage shared-memory ring.  The ring, not the
+// register file, holds the bytes in flight (up to 134 KB per SM): the register-staged kernel above cannot keep more than
+// ~64 KB in flight next to its 52 accumulators and stalls on HBM latency (1.7 ms for 5.4 GB = 3.2 TB/s).
+constexpr int kBwdTile = 64;                                   // rows per stage
+constexpr int kBwdStages = 3;
+constexpr size_t kBwdStageBytes = (size_t)kBwdTile * (2 * kC + kIn) * 4;   // 68,608 B
+constexpr size_t kBwdSmem = kBwdStages * kBwdStageBytes + 64;
+
+__device__ __forceinline__ uint32_t e_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void e_mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(e_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void e_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(e_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void e_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(e_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void e_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(e_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void e_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(e_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(e_smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsE, 1) unit_basic_bwd_tma_kernel(const float *__restrict__ d_basic,
+                                                                          const float *__restrict__ basic,
+                                                                          const float *__restrict__ units, int64_t R,
+                                                                          float *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char e_smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(e_smem + kBwdStages * kBwdStageBytes);
+    uint64_t *empty = full + kBwdStages;
+    __shared__ float s_red[kC][kIn + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (R + kBwdTile - 1) / kBwdTile;
+    const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kBwdStages; ++s) { e_mbar_init(&full[s], 1); e_mbar_init(&empty[s], kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t i) {                              // tile number i of this CTA -> stage i % kBwdStages
+        const int64_t row0 = (blockIdx.x + i * gridDim.x) * kBwdTile;
+        const uint32_t rows = (uint32_t)min((int64_t)kBwdTile, R - row0);
+        unsigned char *st = e_smem + (i % kBwdStages) * kBwdStageBytes;
+        uint64_t *bar = &full[i % kBwdStages];
+        e_mbar_expect_tx(bar, rows * (2 * kC + kIn) * 4);
+        e_bulk_g2s(st, d_basic + row0 * kC, rows * kC * 4, bar);
+        e_bulk_g2s(st + kBwdTile * kC * 4, basic + row0 * kC, rows * kC * 4, bar);
+        e_bulk_g2s(st + 2 * kBwdTile * kC * 4, units + row0 * kIn, rows * kIn * 4, bar);
+    };
+    if (threadIdx.x == 0)
+        for (int64_t i = 0; i < kBwdStages && i < my_tiles; ++i) issue(i);
+
+    float2 acc2[4][kIn / 2];
+    float accb[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        accb[c] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < kIn / 2; ++kk) acc2[c][kk] = make_float2(0.f, 0.f);
+    }
+    for (int64_t i = 0; i < my_tiles; ++i) {
+        const int s = (int)(i % kBwdStages);
+        const uint32_t ph = (uint32_t)((i / kBwdStages) & 1);
+        e_mbar_wait(&full[s], ph);
+        const int64_t row0 = (blockIdx.x + i * gridDim.x) * kBwdTile;
+        const int rows = (int)min((int64_t)kBwdTile, R - row0);
+        const float *sg = reinterpret_cast<const float *>(e_smem + s * kBwdStageBytes);
+        const float *sy = sg + kBwdTile * kC;
+        const float *su = sy + kBwdTile * kC;
+        for (int r = warp; r < rows; r += kWarps) {           // 8 rows per warp per tile
+            const float4 g4 = *reinterpret_cast<const float4 *>(sg + r * kC + lane * 4);
+            const float4 y4 = *reinterpret_cast<const float4 *>(sy + r * kC + lane * 4);
+            const float g[4] = {y4.x > 0.f ? g4.x : 0.f, y4.y > 0.f ? g4.y : 0.f, y4.z > 0.f ? g4.z : 0.f, y4.w > 0.f ? g4.w : 0.f};
+#pragma unroll
+            for (int kk = 0; kk < kIn / 2; ++kk) {
+                const float2 u2 = *reinterpret_cast<const float2 *>(su + r * kIn + 2 * kk);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc2[c][kk] = __ffma2_rn(make_float2(g[c], g[c]), u2, acc2[c][kk]);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) accb[c] += g[c];
+        }
+        __syncwarp();
+        if (lane == 0) e_mbar_arrive(&empty[s]);              // this warp is done with the stage
+        if (threadIdx.x == 0 && i + kBwdStages < my_tiles) {   // refill once all 8 warps have released it
+            e_mbar_wait(&empty[s], ph);
+            issue(i + kBwdStages);
+        }
+    }
+    for (int w = 0; w < kWarps; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int k = 0; k <= kIn; ++k) {
+                    float *dst = &s_red[lane * 4 + c][k];
+                    const float mine = k == kIn ? accb[c] : ((k & 1) ? acc2[c][k >> 1].y : acc2[c][k >> 1].x);
+                    *dst = (w == 0 ? 0.f : *dst) + mine;
+                }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < kC * (kIn + 1); i += kThreadsE)
+        partial[(size_t)blockIdx.x * kC * (kIn + 1) + i] = (&s_red[0][0])[i];
+}
+
 __global__ void unit_basic_bwd_reduce_kernel(const float *__restrict__ partial, int nblocks, float *__restrict__ dw_b,
                                              float *__restrict__ db_b, int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;          // over 128 x 13
@@ -215,11 +329,13 @@ __global__ void __launch_bounds__(kThreadsE) target_unit_bwd_kernel(const float 
     const float g_lo = dlogits[n * kMaxUnits + lane];
     const float g_hi = lane < kMaxUnits - 32 ? dlogits[n * kMaxUnits + 32 + lane] : 0.f;
     const bool any = __any_sync(0xffffffffu, g_lo != 0.f || g_hi != 0.f);
-    float4 *drow = reinterpret_cast<float4 *>(d_ue + n * kMaxUnits * kC) + lane;
+    float4 *drow = d_ue ? reinterpret_cast<float4 *>(d_ue + n * kMaxUnits * kC) + lane : nullptr;   // NULL: d_att only
     float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!any) {                                                   // head unused on this token: exact zeros, no reads
+        if (drow) {
 #pragma unroll 8
-        for (int u = 0; u < kMaxUnits; ++u) drow[u * (kC / 4)] = da;
+            for (int u = 0; u < kMaxUnits; ++u) drow[u * (kC / 4)] = da;
+        }
     } else {
         const float4 a = __ldg(reinterpret_cast<const float4 *>(att + n * kC) + lane);
         const float4 *row = reinterpret_cast<const float4 *>(ue + n * kMaxUnits * kC) + lane;
@@ -228,10 +344,63 @@ __global__ void __launch_bounds__(kThreadsE) target_unit_bwd_kernel(const float 
             const float g = __shfl_sync(0xffffffffu, u < 32 ? g_lo : g_hi, u & 31);
             const float4 v = __ldg(row + u * (kC / 4));
             da.x = fmaf(g, v.x, da.x); da.y = fmaf(g, v.y, da.y); da.z = fmaf(g, v.z, da.z); da.w = fmaf(g, v.w, da.w);
-            drow[u * (kC / 4)] = make_float4(g * a.x, g * a.y, g * a.z, g * a.w);
+            if (drow) drow[u * (kC / 4)] = make_float4(g * a.x, g * a.y, g * a.z, g * a.w);
         }
     }
     *(reinterpret_cast<float4 *>(d_att + n * kC) + lane) = da;
+}
+
+// ---- d(unit embedding) assembled in ONE dense pass ---------------------------------------------------
+// d_ue[n,u,c] = dlogits[n,u] * att[n,c]                      (target-unit head, rank 1; only where the head was used)
+//             + (u == argmax_g[n,c]) ? d_xmax[n,g,c] : 0     (max-pool of group g routes to its arg-max unit)
+// The scattered in-place version (unit_max_bwd) costs a 32-byte sector read+write per 4-byte update -- as much
+// traffic as a dense pass (ncu: 935 MB read / 394 MB written for the 16-unit group) on top of target_unit_bwd's own
+// dense write; fusing the two writes [N,40,128] once.
+__global__ void __launch_bounds__(kThreadsE) unit_grad_assemble_kernel(const float *__restrict__ dlogits,
+                                                                       const float *__restrict__ att,
+                                                                       const float *__restrict__ d_xm, int ld_dx,
+                                                                       const uint8_t *__restrict__ argmax,
+                                                                       float *__restrict__ d_ue, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    float g_lo = 0.f, g_hi = 0.f;
+    if (dlogits) {
+        g_lo = dlogits[n * kMaxUnits + lane];
+        g_hi = lane < kMaxUnits - 32 ? dlogits[n * kMaxUnits + 32 + lane] : 0.f;
+    }
+    const bool any = __any_sync(0xffffffffu, g_lo != 0.f || g_hi != 0.f);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (any) a = __ldg(reinterpret_cast<const float4 *>(att + n * kC) + lane);
+    float4 *drow = reinterpret_cast<float4 *>(d_ue + n * kMaxUnits * kC) + lane;
+    constexpr int units_of[6] = {1, 5, 16, 16, 1, 1};
+    int u = 0;
+#pragma unroll
+    for (int grp = 0; grp < 6; ++grp) {
+        float4 dm = make_float4(0.f, 0.f, 0.f, 0.f);
+        uchar4 idx = make_uchar4(255, 255, 255, 255);
+        if (d_xm && grp < 5) {                                   // group 5 (enemy towers) has no max path (policy.py:127)
+            dm = __ldg(reinterpret_cast<const float4 *>(d_xm + n * ld_dx + grp * kC) + lane);
+            if (grp == 3) {                                       // ... its slot was fed from the enemy non-hero maximum
+                const float4 d2 = __ldg(reinterpret_cast<const float4 *>(d_xm + n * ld_dx + 5 * kC) + lane);
+                dm.x += d2.x; dm.y += d2.y; dm.z += d2.z; dm.w += d2.w;
+            }
+            idx = *reinterpret_cast<const uchar4 *>(argmax + ((int64_t)grp * N + n) * kC + lane * 4);
+        }
+#pragma unroll
+        for (int j = 0; j < units_of[grp]; ++j, ++u) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (any) {
+                const float g = __shfl_sync(0xffffffffu, u < 32 ? g_lo : g_hi, u & 31);
+                o = make_float4(g * a.x, g * a.y, g * a.z, g * a.w);
+            }
+            if (idx.x == j) o.x += dm.x;
+            if (idx.y == j) o.y += dm.y;
+            if (idx.z == j) o.z += dm.z;
+            if (idx.w == j) o.w += dm.w;
+            drow[u * (kC / 4)] = o;
+        }
+    }
 }
 
 int grid_rows(int64_t rows_per_block_iter_unused) { (void)rows_per_block_iter_unused; return 4 * dc_sm_count(); }
@@ -253,11 +422,21 @@ extern "C" int dc_unit_basic_bwd(const float *d_basic, const float *basic, const
                                  int64_t R, int accumulate, void *workspace, dc_stream_t stream) {
     DC_REQUIRE(d_basic && basic && units && dw_b && db_b && workspace && R > 0, DC_EINVAL, "dc_unit_basic_bwd: bad arguments");
     DC_REQUIRE((((uintptr_t)d_basic | (uintptr_t)basic) & 15) == 0, DC_EINVAL, "dc_unit_basic_bwd: inputs must be 16-byte aligned");
-    int blocks = 2 * dc_sm_count();
-    if (blocks > 4 * 1024) blocks = 4 * 1024;
     cudaStream_t st = dc_cu_stream(stream);
     float *partial = reinterpret_cast<float *>(workspace);
-    unit_basic_bwd_kernel<<<blocks, kThreadsE, 0, st>>>(d_basic, basic, units, R, partial);
+    int blocks;
+    if ((((uintptr_t)units) & 15) == 0) {                      // bulk copies need 16-byte aligned sources
+        blocks = dc_sm_count();
+        static bool attr_set = false;
+        if (!attr_set) {
+            DC_CUDA(cudaFuncSetAttribute(unit_basic_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
+            attr_set = true;
+        }
+        unit_basic_bwd_tma_kernel<<<blocks, kThreadsE, kBwdSmem, st>>>(d_basic, basic, units, R, partial);
+    } else {
+        blocks = 2 * dc_sm_count();
+        unit_basic_bwd_kernel<<<blocks, kThreadsE, 0, st>>>(d_basic, basic, units, R, partial);
+    }
     DC_LAUNCH_OK();
     unit_basic_bwd_reduce_kernel<<<(kC * (kIn + 1) + 255) / 256, 256, 0, st>>>(partial, blocks, dw_b, db_b, accumulate);
     DC_LAUNCH_OK();
@@ -297,11 +476,22 @@ extern "C" int dc_target_unit_fwd(const float *att, const float *ue, float *logi
 
 extern "C" int dc_target_unit_bwd(const float *dlogits, const float *att, const float *ue, float *d_att, float *d_ue,
                                   int64_t N, dc_stream_t stream) {
-    DC_REQUIRE(dlogits && att && ue && d_att && d_ue && N > 0, DC_EINVAL, "dc_target_unit_bwd: bad arguments");
+    DC_REQUIRE(dlogits && att && ue && d_att && N > 0, DC_EINVAL, "dc_target_unit_bwd: bad arguments");
     DC_REQUIRE((((uintptr_t)att | (uintptr_t)ue | (uintptr_t)d_att | (uintptr_t)d_ue) & 15) == 0, DC_EINVAL,
                "dc_target_unit_bwd: alignment");
     target_unit_bwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(dlogits, att, ue,
                                                                                                          d_att, d_ue, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_unit_grad_assemble(const float *dlogits, const float *att, const float *d_xmax, int ld_dx,
+                                     const uint8_t *argmax, float *d_ue, int64_t N, dc_stream_t stream) {
+    DC_REQUIRE(d_ue && N > 0 && (!dlogits || att) && (!d_xmax || argmax), DC_EINVAL, "dc_unit_grad_assemble: bad arguments");
+    DC_REQUIRE((((uintptr_t)att | (uintptr_t)d_xmax | (uintptr_t)d_ue) & 15) == 0 && ld_dx % 4 == 0, DC_EINVAL,
+               "dc_unit_grad_assemble: alignment");
+    unit_grad_assemble_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(
+        dlogits, att, d_xmax, ld_dx, argmax, d_ue, N);
     DC_LAUNCH_OK();
     return DC_OK;
 }

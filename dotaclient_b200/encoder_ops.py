@@ -39,6 +39,14 @@ def _wgrad_workspace(No, Ni, device):
     return ws
 
 
+# The unit embedding has two gradient sources: the target-unit head (rank-1, arrives first in backward) and the max-pool
+# (arrives with the pre-rnn gradient, after the recurrence).  When the embedding was produced by UnitEncoder, TargetUnit
+# does not materialise its [N,40,128] gradient: it parks (dlogits, attention) here and UnitEncoder.backward writes the
+# sum of both sources in ONE dense pass (dc_unit_grad_assemble).
+_UE_FROM_ENCODER = set()
+_PENDING_TU = {}
+
+
 def _ptr(t, float_offset=0):
     return t.data_ptr() + 4 * float_offset
 
@@ -86,6 +94,13 @@ class UnitEncoder(torch.autograd.Function):
             basics.append(basic)
         ctx.N = N
         ctx.lead = lead
+        ctx.ue_ptr = ue.data_ptr()
+        ctx.set_materialize_grads(False)               # an absent d_ue must arrive as None, not as 2.7 GB of zeros
+        if any(ctx.needs_input_grad):
+            if len(_UE_FROM_ENCODER) > 64:
+                _UE_FROM_ENCODER.clear()
+                _PENDING_TU.clear()
+            _UE_FROM_ENCODER.add(ctx.ue_ptr)
         ctx.save_for_backward(argmax, *units, *basics, *weights)
         return ue.view(*lead, MAX_UNITS, C), xm.view(*lead, 6 * C)
 
@@ -97,17 +112,25 @@ class UnitEncoder(torch.autograd.Function):
         lib = _lib.load()
         st = _lib.stream_ptr()
         dev = argmax.device
+        pending = _PENDING_TU.pop(ctx.ue_ptr, None)
+        _UE_FROM_ENCODER.discard(ctx.ue_ptr)
+        d_xm = _f32c(d_xm).reshape(N, 6 * C) if d_xm is not None else None
         if d_ue is None:
-            d_ue = torch.zeros((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
+            # one dense pass: rank-1 target-unit part (if that head ran) + max-pool routing
+            d_ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
+            dl, att = pending if pending is not None else (None, None)
+            with PROFILE.span("unit_grad_assemble", 1):
+                _lib.check(lib.dc_unit_grad_assemble(None if dl is None else dl.data_ptr(), None if att is None else att.data_ptr(),
+                                                     None if d_xm is None else d_xm.data_ptr(), 6 * C, argmax.data_ptr(),
+                                                     d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
         else:
             d_ue = _f32c(d_ue).reshape(N, MAX_UNITS, C)          # modified in place below (sole consumer)
-        if d_xm is not None:
-            d_xm = _f32c(d_xm).reshape(N, 6 * C)
-            for g in range(5):
-                copy = _ptr(d_xm, 5 * C) if g == 3 else None
-                with PROFILE.span("unit_max_bwd", 1):
-                    _lib.check(lib.dc_unit_max_bwd(_ptr(d_ue, OFFSETS[g] * C), TOK, _ptr(d_xm, g * C), copy, 6 * C,
-                                                   argmax[g].data_ptr(), N, st), "dc_unit_max_bwd")
+            if d_xm is not None:
+                for g in range(5):
+                    copy = _ptr(d_xm, 5 * C) if g == 3 else None
+                    with PROFILE.span("unit_max_bwd", 1):
+                        _lib.check(lib.dc_unit_max_bwd(_ptr(d_ue, OFFSETS[g] * C), TOK, _ptr(d_xm, g * C), copy, 6 * C,
+                                                       argmax[g].data_ptr(), N, st), "dc_unit_max_bwd")
         dw_b = torch.empty((C, 12), dtype=torch.float32, device=dev)
         db_b = torch.empty(C, dtype=torch.float32, device=dev)
         d_basic = torch.empty((N * max(UNITS), C), dtype=torch.float32, device=dev)
@@ -149,6 +172,7 @@ class TargetUnit(torch.autograd.Function):
                        "dc_target_unit_fwd")
         ctx.save_for_backward(att2, ue2)
         ctx.shapes = (att.shape, ue.shape)
+        ctx.deferred = ue2.data_ptr() in _UE_FROM_ENCODER
         return logits.view(*lead, MAX_UNITS)
 
     @staticmethod
@@ -157,10 +181,14 @@ class TargetUnit(torch.autograd.Function):
         N = att2.shape[0]
         dl = _f32c(dlogits).reshape(N, MAX_UNITS)
         d_att = torch.empty_like(att2)
-        d_ue = torch.empty_like(ue2)
+        d_ue = None if ctx.deferred else torch.empty_like(ue2)
         with PROFILE.span("target_unit_bwd", 1):
             _lib.check(_lib.load().dc_target_unit_bwd(dl.data_ptr(), att2.data_ptr(), ue2.data_ptr(), d_att.data_ptr(),
-                                                      d_ue.data_ptr(), N, _lib.stream_ptr()), "dc_target_unit_bwd")
+                                                      None if d_ue is None else d_ue.data_ptr(), N, _lib.stream_ptr()),
+                       "dc_target_unit_bwd")
+        if ctx.deferred:
+            _PENDING_TU[ue2.data_ptr()] = (dl, att2)            # consumed by UnitEncoder.backward
+            return d_att.view(ctx.shapes[0]), None
         return d_att.view(ctx.shapes[0]), d_ue.view(ctx.shapes[1])
 
 

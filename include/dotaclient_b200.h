@@ -136,6 +136,11 @@ int dc_unit_max_fwd(const float *emb, int64_t tok_stride, int units, float *xmax
                     uint8_t *argmax, int64_t N, dc_stream_t stream);
 int dc_unit_max_bwd(float *d_emb, int64_t tok_stride, const float *d_xmax, const float *d_xmax_copy, int ld_dx,
                     const uint8_t *argmax, int64_t N, dc_stream_t stream);
+/* d_ue[n,u,c] = dlogits[n,u]*att[n,c] + (u == argmax_g[n,c] ? d_xmax[n,g,c] : 0) in one dense pass (either term may
+ * be absent: dlogits == NULL / d_xmax == NULL); argmax is the [5, N, 128] tensor written by dc_unit_max_fwd.
+ * dc_target_unit_bwd accepts d_ue == NULL (d_att only) so that the two gradients of the unit embedding are written once. */
+int dc_unit_grad_assemble(const float *dlogits, const float *att, const float *d_xmax, int ld_dx,
+                          const uint8_t *argmax, float *d_ue, int64_t N, dc_stream_t stream);
 int dc_target_unit_fwd(const float *att, const float *ue, float *logits, int64_t N, dc_stream_t stream);
 int dc_target_unit_bwd(const float *dlogits, const float *att, const float *ue, float *d_att, float *d_ue,
                        int64_t N, dc_stream_t stream);
