@@ -364,7 +364,12 @@ def main():
         barrier()
         return float(ms.item())
 
-    step_dev = lambda: opt.train(batch_dev)          # noqa: E731
+    enqueue = []
+
+    def step_dev():
+        opt.train(batch_dev)
+        enqueue.append(opt.host_enqueue_s)
+
     step_e2e = lambda: opt.train(batch_host)         # noqa: E731
     for _ in range(max(3, args.warmup)):
         step_dev()
@@ -425,7 +430,8 @@ def main():
         "env_steps_per_sec": value * tokens,
         "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 80,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+        "gpu_launches": launches, "host_enqueue_ms_per_step": 1e3 * sum(enqueue[-args.steps:]) / args.steps,
+        "roofline": roofline, "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N=1 only
         log("timing the CPU baseline (oracle port)")

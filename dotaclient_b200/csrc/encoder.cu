@@ -253,6 +253,118 @@ __global__ void unit_basic_bwd_reduce_kernel(const float *__restrict__ partial, 
     *dst = accumulate ? *dst + s : s;
 }
 
+// ---- environment encoder: relu(env W_e^T + b_e), 3 -> 128 (policy.py:55,97) ---------------------------------------
+// Written straight into columns [0,128) of the concatenated pre-rnn input row (row pitch ld), next to the group maxima
+// that unit_max_fwd puts in columns [128,896): the reference's torch.cat (policy.py:129-136) never materialises.
+constexpr int kEnvIn = 3;
+__global__ void __launch_bounds__(kThreadsE) env_fwd_kernel(const float *__restrict__ env, const float *__restrict__ w_e,
+                                                            const float *__restrict__ b_e, float *__restrict__ out, int ld,
+                                                            int64_t N) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float w[4][kEnvIn], b[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        b[c] = b_e[lane * 4 + c];
+#pragma unroll
+        for (int k = 0; k < kEnvIn; ++k) w[c][k] = w_e[(lane * 4 + c) * kEnvIn + k];
+    }
+    const int64_t rows_per_iter = (int64_t)gridDim.x * kWarps * 32;
+    for (int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * 32; base < N; base += rows_per_iter) {
+        const int nrows = (int)min((int64_t)32, N - base);
+        float e[kEnvIn];                                           // lane r holds row base+r, rows are broadcast by shuffle
+#pragma unroll
+        for (int k = 0; k < kEnvIn; ++k) e[k] = lane < nrows ? env[(base + lane) * kEnvIn + k] : 0.f;
+        for (int r = 0; r < nrows; ++r) {
+            float a[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+            for (int k = 0; k < kEnvIn; ++k) {
+                const float u = __shfl_sync(0xffffffffu, e[k], r);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) a[c] = fmaf(u, w[c][k], a[c]);
+            }
+            *reinterpret_cast<float4 *>(out + (base + r) * ld + lane * 4) =
+                make_float4(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f), fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
+        }
+    }
+}
+
+// dW_e, db_e from d_out, the ReLU mask (out > 0) and env: partial[block][128][4] (3 weight columns + bias), then reduced.
+__global__ void __launch_bounds__(kThreadsE) env_bwd_kernel(const float *__restrict__ d_out, const float *__restrict__ out, int ld,
+                                                            const float *__restrict__ env, int64_t N,
+                                                            float *__restrict__ partial) {
+    __shared__ float s_red[kC][kEnvIn + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc[4][kEnvIn + 1];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k <= kEnvIn; ++k) acc[c][k] = 0.f;
+    const int64_t rows_per_iter = (int64_t)gridDim.x * kWarps * 32;
+    for (int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * 32; base < N; base += rows_per_iter) {
+        const int nrows = (int)min((int64_t)32, N - base);
+        float e[kEnvIn];
+#pragma unroll
+        for (int k = 0; k < kEnvIn; ++k) e[k] = lane < nrows ? env[(base + lane) * kEnvIn + k] : 0.f;
+        for (int r0 = 0; r0 < nrows; r0 += 8) {                    // 8 rows per trip: 16 independent 16-byte loads per lane
+            float4 g4[8], y4[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = min(r0 + j, nrows - 1);
+                g4[j] = __ldg(reinterpret_cast<const float4 *>(d_out + (base + r) * ld) + lane);
+                y4[j] = __ldg(reinterpret_cast<const float4 *>(out + (base + r) * ld) + lane);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool live = r0 + j < nrows;                  // uniform across the warp
+                const float g[4] = {live && y4[j].x > 0.f ? g4[j].x : 0.f, live && y4[j].y > 0.f ? g4[j].y : 0.f,
+                                    live && y4[j].z > 0.f ? g4[j].z : 0.f, live && y4[j].w > 0.f ? g4[j].w : 0.f};
+#pragma unroll
+                for (int k = 0; k < kEnvIn; ++k) {
+                    const float u = __shfl_sync(0xffffffffu, e[k], min(r0 + j, 31));
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c][k] = fmaf(g[c], u, acc[c][k]);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c][kEnvIn] += g[c];
+            }
+        }
+    }
+    for (int w = 0; w < kWarps; ++w) {                             // fixed fold order: deterministic
+        if (warp == w) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int k = 0; k <= kEnvIn; ++k) {
+                    float *dst = &s_red[lane * 4 + c][k];
+                    *dst = (w == 0 ? 0.f : *dst) + acc[c][k];
+                }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < kC * (kEnvIn + 1); i += kThreadsE)
+        partial[(size_t)blockIdx.x * kC * (kEnvIn + 1) + i] = (&s_red[0][0])[i];
+}
+
+// 32 outputs x 8 block-groups per CTA: group y sums blocks y, y+8, ...; the groups are then added in order.
+__global__ void __launch_bounds__(256) env_bwd_reduce_kernel(const float *__restrict__ partial, int nblocks, float *__restrict__ dw_e,
+                                                             float *__restrict__ db_e) {
+    __shared__ float sh[8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;                             // over 128 x 4
+    float s = 0.f;
+    if (i < kC * (kEnvIn + 1))
+        for (int b = y; b < nblocks; b += 8) s += partial[(size_t)b * kC * (kEnvIn + 1) + i];
+    sh[y][x] = s;
+    __syncthreads();
+    if (y == 0 && i < kC * (kEnvIn + 1)) {
+        float t = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += sh[r][x];
+        const int o = i / (kEnvIn + 1), k = i % (kEnvIn + 1);
+        if (k < kEnvIn) dw_e[o * kEnvIn + k] = t; else db_e[o] = t;
+    }
+}
+
 // ---- max over the units of one group --------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsE) unit_max_fwd_kernel(const float *__restrict__ emb, int64_t tok_stride,
                                                                  int units, float *__restrict__ xmax, int ld_x,
@@ -439,6 +551,32 @@ extern "C" int dc_unit_basic_bwd(const float *d_basic, const float *basic, const
     }
     DC_LAUNCH_OK();
     unit_basic_bwd_reduce_kernel<<<(kC * (kIn + 1) + 255) / 256, 256, 0, st>>>(partial, blocks, dw_b, db_b, accumulate);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_env_fwd(const float *env, const float *w_e, const float *b_e, float *out, int ld_out, int64_t N,
+                          dc_stream_t stream) {
+    DC_REQUIRE(env && w_e && b_e && out && N > 0 && ld_out >= kC && ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0, DC_EINVAL,
+               "dc_env_fwd: bad arguments");
+    env_fwd_kernel<<<grid_rows(0), kThreadsE, 0, dc_cu_stream(stream)>>>(env, w_e, b_e, out, ld_out, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" size_t dc_env_bwd_workspace_bytes(void) { return (size_t)1024 * kC * (kEnvIn + 1) * sizeof(float); }
+
+extern "C" int dc_env_bwd(const float *d_out, const float *out, int ld, const float *env, float *dw_e, float *db_e, int64_t N,
+                          void *workspace, dc_stream_t stream) {
+    DC_REQUIRE(d_out && out && env && dw_e && db_e && workspace && N > 0 && ld >= kC && ld % 4 == 0, DC_EINVAL,
+               "dc_env_bwd: bad arguments");
+    DC_REQUIRE((((uintptr_t)d_out | (uintptr_t)out) & 15) == 0, DC_EINVAL, "dc_env_bwd: inputs must be 16-byte aligned");
+    cudaStream_t st = dc_cu_stream(stream);
+    float *partial = reinterpret_cast<float *>(workspace);
+    const int blocks = 2 * dc_sm_count();                          // <= 1024 (workspace bound)
+    env_bwd_kernel<<<blocks, kThreadsE, 0, st>>>(d_out, out, ld, env, N, partial);
+    DC_LAUNCH_OK();
+    env_bwd_reduce_kernel<<<(kC * (kEnvIn + 1) + 31) / 32, 256, 0, st>>>(partial, blocks, dw_e, db_e);
     DC_LAUNCH_OK();
     return DC_OK;
 }

@@ -23,6 +23,7 @@
 // Tensor-pipe work: 2*M*N*K*3 flops; HBM: 4*(M*K + N*K + M*N) bytes.  For the K=128 GEMMs of this model the
 // kernel is HBM-bound even with the 3x flops.
 #include "dc_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -417,6 +418,198 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
 }
 
 // =================================================================================================
+// K <= 128, A operand in TENSOR MEMORY.  ncu on the resident-B kernel: tensor pipe 39 %, DRAM 49 %, nothing saturated
+// except shared memory -- with the 3xTF32 split every k-step reads the A tile from shared memory three times and the
+// producers write it there twice (hi, lo).  Here the producers put A_hi / A_lo straight from registers into TMEM
+// (tcgen05.st, one TMEM lane = one tile row per thread) and the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc);
+// shared memory only holds the resident B block.  TMEM map (512 columns): [0,256) two accumulators, [256,512) four A
+// stages of 64 columns (32 hi + 32 lo = one 32-float k-chunk).
+constexpr int kAStages = 4;
+constexpr int kAStageCols = 64;
+constexpr size_t kSmemBytesATmem = (size_t)kMaxResChunks * 2 * kTileBytes + 1024 + 128;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+// one tile row per thread: 32 consecutive floats of row `row` (zero beyond rows_total), four 256-bit loads
+__device__ __forceinline__ void row_load32(const float *__restrict__ src, RowMap map, int row, int rows_total, int k0, float (&v)[32]) {
+    if (row < rows_total) {
+        const float *p = src + map.off(row) + k0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(v[8 * q]), "=f"(v[8 * q + 1]), "=f"(v[8 * q + 2]), "=f"(v[8 * q + 3]), "=f"(v[8 * q + 4]),
+                           "=f"(v[8 * q + 5]), "=f"(v[8 * q + 6]), "=f"(v[8 * q + 7])
+                         : "l"(p + 8 * q));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const float *__restrict__ A, RowMap amap,
+                                                                        const float *__restrict__ B, int ldb,
+                                                                        const float *__restrict__ bias, float *__restrict__ C,
+                                                                        RowMap cmap, int M, int N, int K, int relu, bool wide) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *bres = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bres + (size_t)kMaxResChunks * 2 * kTileBytes);
+    uint64_t *full = bars, *empty = bars + kAStages, *acc_full = bars + 2 * kAStages, *acc_empty = bars + 2 * kAStages + 2;
+    uint64_t *b_ready = bars + 2 * kAStages + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kAStages + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
+    const int n_blk = blockIdx.x % n_blocks, m_first = blockIdx.x / n_blocks, m_step = gridDim.x / n_blocks;
+    const int n0 = n_blk * BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kAStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        mbar_init(b_ready, kProducerThreads * kProducerGroups / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a0 = tmem_base + 2 * kAccCols;
+
+    if (warp < kMmaWarp) {
+        // ===== PRODUCERS =====
+        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
+        for (int kc = g; kc < k_chunks; kc += kProducerGroups)            // resident B block (shared memory), once
+            produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
+                         bres + (size_t)kc * 2 * kTileBytes + kTileBytes, t);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(b_ready);
+        const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
+        const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
+        const int row_in_tile = (warp & 3) * 32 + lane;                   // == the TMEM lane this thread may write
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        // Two register buffers in ping-pong: a buffer is refilled (chunk + 2 rounds ahead) the moment it has been written
+        // to TMEM, so both are in flight except while one is being split -- ~96 KB of loads outstanding per SM.
+        float va[32], vb[32];
+        auto fetch = [&](uint32_t cc, float (&buf)[32]) {
+            if (cc < total_chunks)
+                row_load32(A, amap, (m_first + (int)(cc / k_chunks) * m_step) * BM + row_in_tile, M, (int)(cc % k_chunks) * BK, buf);
+        };
+        auto emit = [&](uint32_t cc, const float (&buf)[32]) {
+            const int stage = cc % kAStages;
+            mbar_wait(&empty[stage], ((cc / kAStages) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tcol = tmem_a0 + stage * kAStageCols + lane_addr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { hi[jj] = tf32_rna(buf[8 * q + jj]); lo[jj] = buf[8 * q + jj] - hi[jj]; }
+                tmem_st8(tcol + 8 * q, hi);
+                tmem_st8(tcol + 32 + 8 * q, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+        };
+        fetch(g, va);
+        fetch(g + kProducerGroups, vb);
+        for (uint32_t c = g; c < total_chunks; c += 2 * kProducerGroups) {
+            emit(c, va);
+            fetch(c + 2 * kProducerGroups, va);
+            if (c + kProducerGroups < total_chunks) {
+                emit(c + kProducerGroups, vb);
+                fetch(c + 3 * kProducerGroups, vb);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA ISSUER =====
+        mbar_wait(b_ready, 0);
+        uint32_t c = 0;
+        int it = 0;
+        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
+            const int a = it & 1;
+            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + a * kAccCols;
+            for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+                const int stage = c % kAStages;
+                mbar_wait(&full[stage], (c / kAStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t a_hi = tmem_a0 + stage * kAStageCols, a_lo = a_hi + 32;
+                    const uint32_t bbase = smem_u32(bres + (size_t)kc * 2 * kTileBytes);
+                    const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + kTileBytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t first = (kc | ks) != 0;
+                        umma_tf32_ts(tmem_d, a_lo + 8 * ks, b_hi + adv, kIdesc, first);
+                        umma_tf32_ts(tmem_d, a_hi + 8 * ks, b_lo + adv, kIdesc, 1u);
+                        umma_tf32_ts(tmem_d, a_hi + 8 * ks, b_hi + adv, kIdesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kc == k_chunks - 1) umma_commit(&acc_full[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== EPILOGUE =====
+        const int q = warp & 3;
+        int it = 0;
+        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
+            const int a = it & 1;
+            const int m0 = mb * BM;
+            mbar_wait(&acc_full[a], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + q * 32 + lane;
+            float *crow = C + cmap.off(row < M ? row : 0) + n0;
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kAccCols + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// =================================================================================================
 // Weight-gradient GEMM:  dW[No, Ni] = dY[T, No]^T * X[T, Ni]   and   db[No] = column sums of dY.
 //
 // The contraction runs over the TOKEN dimension, so both operands are MN-major in memory (features contiguous).
@@ -595,27 +788,47 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
     }
 }
 
-// dW[o][i] (+)= sum_split part_w[split][tile][o%128][i%128];  db[o] (+)= sum_split part_b[split][o]   (fixed order)
-__global__ void wgrad_reduce_kernel(const float *__restrict__ part_w, const float *__restrict__ part_b, int nsplit, int No,
-                                    int Ni, float *__restrict__ dW, int ldw, float *__restrict__ db, int accumulate) {
+// dW[o][i] (+)= sum_split part_w[split][tile][o%128][i%128];  db[o] (+)= sum_split part_b[split][o].
+// One float4 of [dW | db] per thread column, the splits dealt to 8 thread rows (s = y, y+8, ...) whose partial sums are
+// then added in row order: a fixed summation tree (deterministic) with 8x the loads in flight of a serial loop.
+constexpr int kRedRows = 8;
+__global__ void __launch_bounds__(32 * kRedRows) wgrad_reduce_kernel(const float *__restrict__ part_w, const float *__restrict__ part_b,
+                                                                     int nsplit, int No, int Ni, float *__restrict__ dW, int ldw,
+                                                                     float *__restrict__ db, int accumulate) {
+    __shared__ float4 sh[kRedRows][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;           // one float4 of dW per thread
-    const int total4 = No * Ni / 4;
+    const int total4 = No * Ni / 4, bias4 = db != nullptr ? No / 4 : 0;
+    const int idx = blockIdx.x * 32 + x;
+    const float *src = nullptr;
+    float *dst = nullptr;
+    size_t stride = 0;
     if (idx < total4) {
         const int o = (idx * 4) / Ni, i = (idx * 4) % Ni;
         const int tile = (o / BM) * n_blocks + i / BN;
-        const size_t base = ((size_t)tile * BM + o % BM) * BN + i % BN;
-        float4 acc = accumulate ? *reinterpret_cast<const float4 *>(dW + (size_t)o * ldw + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < nsplit; ++s) {
-            const float4 v = *reinterpret_cast<const float4 *>(part_w + (size_t)s * tiles_mn * BM * BN + base);
+        src = part_w + ((size_t)tile * BM + o % BM) * BN + i % BN;
+        stride = (size_t)tiles_mn * BM * BN;
+        dst = dW + (size_t)o * ldw + i;
+    } else if (idx < total4 + bias4) {
+        src = part_b + (size_t)(idx - total4) * 4;
+        stride = (size_t)No;
+        dst = db + (size_t)(idx - total4) * 4;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src != nullptr) {
+#pragma unroll 4
+        for (int s = y; s < nsplit; s += kRedRows) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (size_t)s * stride));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        *reinterpret_cast<float4 *>(dW + (size_t)o * ldw + i) = acc;
     }
-    if (db != nullptr && idx < No) {
-        float acc = accumulate ? db[idx] : 0.f;
-        for (int s = 0; s < nsplit; ++s) acc += part_b[(size_t)s * No + idx];
-        db[idx] = acc;
+    sh[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && dst != nullptr) {
+        float4 t = accumulate ? *reinterpret_cast<const float4 *>(dst) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kRedRows; ++r) { t.x += sh[r][x].x; t.y += sh[r][x].y; t.z += sh[r][x].z; t.w += sh[r][x].w; }
+        *reinterpret_cast<float4 *>(dst) = t;
     }
 }
 
@@ -651,6 +864,20 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
         }
         int per_col = dc_sm_count() / n_blocks;                          // CTAs per column block
         if (per_col > m_blocks) per_col = m_blocks;
+        static int use_atmem = -1;                                        // DC_GEMM_ATMEM=0 keeps A in shared memory
+        if (use_atmem < 0) { const char *e = getenv("DC_GEMM_ATMEM"); use_atmem = (e && e[0] == '0') ? 0 : 1; }
+        const bool rows32 = ((uintptr_t)A & 31) == 0 && lda % 8 == 0 && (amap.rpb == 0 || amap.bs % 8 == 0);   // 256-bit row loads
+        if (use_atmem && rows32) {
+            static bool attr_t = false;
+            if (!attr_t) {
+                DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesATmem));
+                attr_t = true;
+            }
+            gemm_tf32x3_atmem_kernel<<<per_col * n_blocks, kThreads, kSmemBytesATmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
+                                                                                                          (int)M, N, K, relu, wide);
+            DC_LAUNCH_OK();
+            return DC_OK;
+        }
         gemm_tf32x3_bres_kernel<<<per_col * n_blocks, kThreads, kSmemBytesBRes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
                                                                                                        (int)M, N, K, relu, wide);
         DC_LAUNCH_OK();
@@ -682,7 +909,8 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
                "dc_gemm_wgrad_tf32x3: need No %% 128 == 0 and Ni %% 128 == 0 (T=%lld No=%d Ni=%d)", (long long)T, No, Ni);
     DC_REQUIRE(ldy >= No && ldx >= Ni && ldw >= Ni && ldy % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0, DC_EINVAL,
                "dc_gemm_wgrad_tf32x3: bad leading dimension");
-    DC_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)dW & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+    DC_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)dW & 15) == 0 && ((uintptr_t)workspace & 15) == 0 &&
+                   ((uintptr_t)db & 15) == 0,
                DC_EINVAL, "dc_gemm_wgrad_tf32x3: pointers must be 16-byte aligned");
     const size_t smem = kSmemBytes + kMmaWarp * 128 * sizeof(float);
     static bool attr_set = false;
@@ -696,8 +924,8 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
     cudaStream_t st = dc_cu_stream(stream);
     gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
     DC_LAUNCH_OK();
-    const int total4 = No * Ni / 4;
-    wgrad_reduce_kernel<<<(total4 + 255) / 256, 256, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);
+    const int total4 = No * Ni / 4 + (db ? No / 4 : 0);
+    wgrad_reduce_kernel<<<(total4 + 31) / 32, 32 * kRedRows, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);
     DC_LAUNCH_OK();
     return DC_OK;
 }

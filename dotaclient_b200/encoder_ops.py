@@ -15,6 +15,7 @@ OFFSETS = (0, 1, 6, 22, 38, 39)
 MAX_UNITS = 40
 C = 128
 TOK = MAX_UNITS * C                        # floats per token in the unit-embedding tensor
+XCAT = 7 * C                               # pre-rnn input row: env encoding + six group maxima (policy.py:129-136)
 
 _basic_ws = {}
 
@@ -24,6 +25,17 @@ def _basic_workspace(device):
     if ws is None:
         ws = torch.empty(int(_lib.load().dc_unit_basic_bwd_workspace_bytes()), dtype=torch.uint8, device=device)
         _basic_ws[device] = ws
+    return ws
+
+
+_env_ws = {}
+
+
+def _env_workspace(device):
+    ws = _env_ws.get(device)
+    if ws is None:
+        ws = torch.empty(int(_lib.load().dc_env_bwd_workspace_bytes()), dtype=torch.uint8, device=device)
+        _env_ws[device] = ws
     return ws
 
 
@@ -52,15 +64,16 @@ def _ptr(t, float_offset=0):
 
 
 class UnitEncoder(torch.autograd.Function):
-    """(w_b, b_b, units x6, W_g x6, b_g x6) -> unit embedding ``[..., 40, 128]`` and the six group maxima ``[..., 768]``.
+    """(env, w_e, b_e, w_b, b_b, units x6, W_g x6, b_g x6) -> unit embedding ``[..., 40, 128]`` and the pre-rnn input row
+    ``[..., 896]`` = relu(affine_env(env)) followed by the six group maxima, written in place by the kernels (no cat).
 
     maxima slot 5 (enemy towers) is a copy of slot 3 (enemy non-heroes): the reference's ``policy.py:127``.
     """
 
     @staticmethod
-    def forward(ctx, w_b, b_b, *rest):
+    def forward(ctx, env, w_e, b_e, w_b, b_b, *rest):
         units, weights, biases = rest[:6], rest[6:12], rest[12:18]
-        _need_cuda(w_b, *units)
+        _need_cuda(env, w_b, *units)
         lib = _lib.load()
         st = _lib.stream_ptr()
         lead = units[0].shape[:-2]
@@ -73,8 +86,13 @@ class UnitEncoder(torch.autograd.Function):
         weights = [_f32c(w.detach()) for w in weights]
         biases = [_f32c(b.detach()) for b in biases]
         ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
-        xm = torch.empty((N, 6 * C), dtype=torch.float32, device=dev)
+        xcat = torch.empty((N, XCAT), dtype=torch.float32, device=dev)
         argmax = torch.empty((5, N, C), dtype=torch.uint8, device=dev)
+        env2 = _f32c(env.detach()).reshape(N, 3)
+        w_e, b_e = _f32c(w_e.detach()), _f32c(b_e.detach())
+        wait_h2d(env2)
+        with PROFILE.span("env_fwd", 1):
+            _lib.check(lib.dc_env_fwd(env2.data_ptr(), w_e.data_ptr(), b_e.data_ptr(), xcat.data_ptr(), XCAT, N, st), "dc_env_fwd")
         basics = []
         for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
             R = N * n_u
@@ -87,9 +105,9 @@ class UnitEncoder(torch.autograd.Function):
                 _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, weights[g].data_ptr(), C, biases[g].data_ptr(),
                                                       _ptr(ue, off * C), C, n_u, TOK, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
             if g < 5:
-                copy = _ptr(xm, 5 * C) if g == 3 else None
+                copy = _ptr(xcat, 6 * C) if g == 3 else None
                 with PROFILE.span("unit_max_fwd", 1):
-                    _lib.check(lib.dc_unit_max_fwd(_ptr(ue, off * C), TOK, n_u, _ptr(xm, g * C), copy, 6 * C,
+                    _lib.check(lib.dc_unit_max_fwd(_ptr(ue, off * C), TOK, n_u, _ptr(xcat, (g + 1) * C), copy, XCAT,
                                                    argmax[g].data_ptr(), N, st), "dc_unit_max_fwd")
             basics.append(basic)
         ctx.N = N
@@ -101,35 +119,44 @@ class UnitEncoder(torch.autograd.Function):
                 _UE_FROM_ENCODER.clear()
                 _PENDING_TU.clear()
             _UE_FROM_ENCODER.add(ctx.ue_ptr)
-        ctx.save_for_backward(argmax, *units, *basics, *weights)
-        return ue.view(*lead, MAX_UNITS, C), xm.view(*lead, 6 * C)
+        ctx.save_for_backward(argmax, *units, *basics, *weights, env2, xcat)
+        return ue.view(*lead, MAX_UNITS, C), xcat.view(*lead, XCAT)
 
     @staticmethod
-    def backward(ctx, d_ue, d_xm):
+    def backward(ctx, d_ue, d_xcat):
         saved = ctx.saved_tensors
-        argmax, units, basics, weights = saved[0], saved[1:7], saved[7:13], saved[13:19]
+        argmax, units, basics, weights, env2, xcat = saved[0], saved[1:7], saved[7:13], saved[13:19], saved[19], saved[20]
         N = ctx.N
         lib = _lib.load()
         st = _lib.stream_ptr()
         dev = argmax.device
         pending = _PENDING_TU.pop(ctx.ue_ptr, None)
         _UE_FROM_ENCODER.discard(ctx.ue_ptr)
-        d_xm = _f32c(d_xm).reshape(N, 6 * C) if d_xm is not None else None
+        dw_e = db_e = None
+        d_xm = None                                    # the maxima part of d_xcat, addressed in place (row pitch 896)
+        if d_xcat is not None:
+            d_xcat = _f32c(d_xcat).reshape(N, XCAT)
+            d_xm = _ptr(d_xcat, C)
+            dw_e = torch.empty((C, 3), dtype=torch.float32, device=dev)
+            db_e = torch.empty(C, dtype=torch.float32, device=dev)
+            with PROFILE.span("env_bwd", 2):
+                _lib.check(lib.dc_env_bwd(d_xcat.data_ptr(), xcat.data_ptr(), XCAT, env2.data_ptr(), dw_e.data_ptr(), db_e.data_ptr(),
+                                          N, _env_workspace(dev).data_ptr(), st), "dc_env_bwd")
         if d_ue is None:
             # one dense pass: rank-1 target-unit part (if that head ran) + max-pool routing
             d_ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
             dl, att = pending if pending is not None else (None, None)
             with PROFILE.span("unit_grad_assemble", 1):
                 _lib.check(lib.dc_unit_grad_assemble(None if dl is None else dl.data_ptr(), None if att is None else att.data_ptr(),
-                                                     None if d_xm is None else d_xm.data_ptr(), 6 * C, argmax.data_ptr(),
+                                                     d_xm, XCAT, argmax.data_ptr(),
                                                      d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
         else:
             d_ue = _f32c(d_ue).reshape(N, MAX_UNITS, C)          # modified in place below (sole consumer)
             if d_xm is not None:
                 for g in range(5):
-                    copy = _ptr(d_xm, 5 * C) if g == 3 else None
+                    copy = d_xm + 4 * 5 * C if g == 3 else None
                     with PROFILE.span("unit_max_bwd", 1):
-                        _lib.check(lib.dc_unit_max_bwd(_ptr(d_ue, OFFSETS[g] * C), TOK, _ptr(d_xm, g * C), copy, 6 * C,
+                        _lib.check(lib.dc_unit_max_bwd(_ptr(d_ue, OFFSETS[g] * C), TOK, d_xm + 4 * g * C, copy, XCAT,
                                                        argmax[g].data_ptr(), N, st), "dc_unit_max_bwd")
         dw_b = torch.empty((C, 12), dtype=torch.float32, device=dev)
         db_b = torch.empty(C, dtype=torch.float32, device=dev)
@@ -154,7 +181,7 @@ class UnitEncoder(torch.autograd.Function):
                                                  db_b.data_ptr(), R, 1 if g > 0 else 0, ws_b.data_ptr(), st), "dc_unit_basic_bwd")
             dws.append(dw)
             dbs.append(db)
-        return (dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
+        return (None, dw_e, db_e, dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
 
 
 class TargetUnit(torch.autograd.Function):
@@ -192,8 +219,9 @@ class TargetUnit(torch.autograd.Function):
         return d_att.view(ctx.shapes[0]), d_ue.view(ctx.shapes[1])
 
 
-def unit_encoder(w_b, b_b, units, weights, biases):
-    return UnitEncoder.apply(w_b, b_b, *units, *weights, *biases)
+def unit_encoder(env, w_e, b_e, w_b, b_b, units, weights, biases):
+    """-> (unit embedding ``[..., 40, 128]``, pre-rnn input ``[..., 896]``)."""
+    return UnitEncoder.apply(env, w_e, b_e, w_b, b_b, *units, *weights, *biases)
 
 
 def target_unit(att, ue):

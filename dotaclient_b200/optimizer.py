@@ -502,6 +502,7 @@ class DotaOptimizer:
         else:
             batch = ExperienceBatch.from_sequences(experiences, self.device)
         keys = ops.HEAD_KEYS
+        t_enter = time.perf_counter()
         self.flat.zero_grad()                                             # :671
         hidden = (batch.h0, batch.c0) if self.policy_base.cell == "lstm" else batch.h0
         ddp = self.policy if isinstance(self.policy, DistributedDataParallelSparseParamCPU) else None
@@ -537,6 +538,7 @@ class DotaOptimizer:
         host = self._host_result
         host[:_lib.LOSS_SLOTS].copy_(out, non_blocking=True)
         host[_lib.LOSS_SLOTS:].copy_(self._metrics, non_blocking=True)
+        self.host_enqueue_s = time.perf_counter() - t_enter   # host time to launch the step (the GPU runs behind it)
         torch.cuda.current_stream().synchronize()      # the step's single host sync (result read-back)
         res = host.clone()
         if res[_lib.LOSS_SLOTS + 3] != 0:               # :667-669, :678-679 (parameters were left untouched)

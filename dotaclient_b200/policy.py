@@ -120,10 +120,10 @@ class Policy(nn.Module):
         if ops._TC_ENABLED and env.is_cuda:
             # explicit kernel chain (csrc/encoder.cu + tcgen05 GEMMs): no torch.cat, sparse max-pool backward
             layers = [getattr(self, "affine_unit_" + s) for s, _, _ in UNIT_GROUPS]
-            unit_embedding, xmax = encoder_ops.unit_encoder(
+            unit_embedding, x = encoder_ops.unit_encoder(
+                env, self.affine_env.weight, self.affine_env.bias,
                 self.affine_unit_basic_stats.weight, self.affine_unit_basic_stats.bias, list(groups),
                 [l.weight for l in layers], [l.bias for l in layers])
-            x = torch.cat([F.relu(self.affine_env(env)), xmax], dim=-1)
             return ops.linear(x, self.affine_pre_rnn.weight, self.affine_pre_rnn.bias, relu=True), unit_embedding
         emb, emb_max = {}, {}
         for (suffix, _, _), units in zip(UNIT_GROUPS, groups):

@@ -132,6 +132,14 @@ int dc_unit_basic_fwd(const float *units, const float *w_b, const float *b_b, fl
 size_t dc_unit_basic_bwd_workspace_bytes(void);
 int dc_unit_basic_bwd(const float *d_basic, const float *basic, const float *units, float *dw_b, float *db_b,
                       int64_t R, int accumulate, void *workspace, dc_stream_t stream);
+/* Environment encoder (policy.py:55,97): out[n*ld_out + c] = relu(env[n,:3] . W_e[c,:] + b_e[c]), c < 128 -- written into
+ * columns [0,128) of the concatenated pre-rnn input row (ld_out = 896), so the reference's torch.cat (policy.py:129-136)
+ * is never materialised.  dc_env_bwd: dW_e[128,3] = (d_out * (out>0))^T env, db_e[128] = column sums (deterministic). */
+int dc_env_fwd(const float *env, const float *w_e, const float *b_e, float *out, int ld_out, int64_t N,
+               dc_stream_t stream);
+size_t dc_env_bwd_workspace_bytes(void);
+int dc_env_bwd(const float *d_out, const float *out, int ld, const float *env, float *dw_e, float *db_e, int64_t N,
+               void *workspace, dc_stream_t stream);
 int dc_unit_max_fwd(const float *emb, int64_t tok_stride, int units, float *xmax, float *xmax_copy, int ld_x,
                     uint8_t *argmax, int64_t N, dc_stream_t stream);
 int dc_unit_max_bwd(float *d_emb, int64_t tok_stride, const float *d_xmax, const float *d_xmax_copy, int ld_dx,

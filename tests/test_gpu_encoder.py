@@ -12,36 +12,41 @@ pytestmark = pytest.mark.gpu
 UNITS = (1, 5, 16, 16, 1, 1)
 
 
-def _reference(w_b, b_b, units, weights, biases):
+def _reference(env, w_e, b_e, w_b, b_b, units, weights, biases):
     emb = [F.linear(F.relu(F.linear(u, w_b, b_b)), w, b) for u, w, b in zip(units, weights, biases)]
     mx = [e.max(dim=-2)[0] for e in emb]
     mx[5] = mx[3]                                        # policy.py:127
-    return torch.cat(emb, dim=-2), torch.cat(mx, dim=-1)
+    return torch.cat(emb, dim=-2), torch.cat([F.relu(F.linear(env, w_e, b_e))] + mx, dim=-1)   # policy.py:97,129-136
 
 
 @pytest.mark.parametrize("lead", [(7,), (3, 5), (1,), (130,)])
 def test_unit_encoder_forward_backward(lead):
     from dotaclient_b200 import encoder_ops
     g = torch.Generator().manual_seed(sum(lead))
+    env = torch.randn(*lead, 3, generator=g)
+    w_e = (torch.randn(128, 3, generator=g) * 0.5).requires_grad_(True)
+    b_e = (torch.randn(128, generator=g) * 0.1).requires_grad_(True)
     w_b = (torch.randn(128, 12, generator=g) * 0.3).requires_grad_(True)
     b_b = (torch.randn(128, generator=g) * 0.1).requires_grad_(True)
     units = [torch.randn(*lead, n, 12, generator=g) for n in UNITS]
     weights = [(torch.randn(128, 128, generator=g) * 0.1).requires_grad_(True) for _ in UNITS]
     biases = [(torch.randn(128, generator=g) * 0.1).requires_grad_(True) for _ in UNITS]
-    ue_r, xm_r = _reference(w_b, b_b, units, weights, biases)
+    ue_r, xm_r = _reference(env, w_e, b_e, w_b, b_b, units, weights, biases)
     g_ue = torch.randn(ue_r.shape, generator=g)
     g_xm = torch.randn(xm_r.shape, generator=g)
     ((ue_r * g_ue).sum() + (xm_r * g_xm).sum()).backward()
 
     d = torch.device("cuda", 0)
     params = [t.detach().clone().to(d).requires_grad_(True) for t in [w_b, b_b] + weights + biases]
-    ue, xm = encoder_ops.unit_encoder(params[0], params[1], [u.to(d) for u in units], params[2:8], params[8:14])
+    pe = [t.detach().clone().to(d).requires_grad_(True) for t in (w_e, b_e)]
+    ue, xm = encoder_ops.unit_encoder(env.to(d), pe[0], pe[1], params[0], params[1], [u.to(d) for u in units], params[2:8],
+                                      params[8:14])
     assert ue.shape == ue_r.shape and xm.shape == xm_r.shape
     torch.testing.assert_close(ue.detach().cpu(), ue_r.detach(), rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(xm.detach().cpu(), xm_r.detach(), rtol=1e-4, atol=2e-5)
     ((ue * g_ue.to(d)).sum() + (xm * g_xm.to(d)).sum()).backward()
     n_tok = ue_r.numel() // (40 * 128)
-    for mine, ref in zip(params, [w_b, b_b] + weights + biases):
+    for mine, ref in zip(params + pe, [w_b, b_b] + weights + biases + [w_e, b_e]):
         torch.testing.assert_close(mine.grad.cpu(), ref.grad, rtol=2e-4, atol=2e-6 * max(1, n_tok) * 16)
 
 
@@ -55,10 +60,15 @@ def test_unit_max_tie_breaking_and_grad_routing():
     weights = [torch.eye(128) for _ in UNITS]
     biases = [torch.zeros(128) for _ in UNITS]
     params = [t.to(d).requires_grad_(True) for t in [w_b, b_b] + weights + biases]
-    ue, xm = encoder_ops.unit_encoder(params[0], params[1], [u.to(d) for u in units], params[2:8], params[8:14])
+    w_e, b_e = torch.zeros(128, 3, device=d, requires_grad=True), torch.full((128,), -1.0, device=d, requires_grad=True)
+    ue, xcat = encoder_ops.unit_encoder(torch.randn(4, 3, device=d), w_e, b_e, params[0], params[1], [u.to(d) for u in units],
+                                        params[2:8], params[8:14])
+    xm = xcat[..., 128:]
     assert torch.equal(xm, torch.ones_like(xm))
+    assert torch.equal(xcat[..., :128], torch.zeros_like(xcat[..., :128]))      # relu(-1) == 0: a dead env encoder ...
     ue.retain_grad()
-    xm.sum().backward()
+    xcat.sum().backward()
+    assert float(w_e.grad.abs().sum()) == 0.0 and float(b_e.grad.abs().sum()) == 0.0   # ... receives no gradient
     # bias gradient of group g == number of tokens routed to it: only unit 0 of each group gets d(max)
     for gidx in range(5):
         expect = 4.0 * (2.0 if gidx == 3 else 1.0)         # enh also receives the enemy-tower slot's gradient
