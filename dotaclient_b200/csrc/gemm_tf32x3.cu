@@ -418,15 +418,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
 }
 
 // =================================================================================================
-// K <= 128, A operand in TENSOR MEMORY.  ncu on the resident-B kernel: tensor pipe 39 %, DRAM 49 %, nothing saturated
-// except shared memory -- with the 3xTF32 split every k-step reads the A tile from shared memory three times and the
-// producers write it there twice (hi, lo).  Here the producers put A_hi / A_lo straight from registers into TMEM
-// (tcgen05.st, one TMEM lane = one tile row per thread) and the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc);
-// shared memory only holds the resident B block.  TMEM map (512 columns): [0,256) two accumulators, [256,512) four A
-// stages of 64 columns (32 hi + 32 lo = one 32-float k-chunk).
-constexpr int kAStages = 4;
-constexpr int kAStageCols = 64;
-constexpr size_t kSmemBytesATmem = (size_t)kMaxResChunks * 2 * kTileBytes + 1024 + 128;
+// K <= 128, WEIGHTS IN TENSOR MEMORY, transposed product.  D^T[feature][token] = W[feature][k] . X[token][k]:
+//   * the 128 x K weight block (hi and lo halves) is written ONCE per CTA into TMEM (tcgen05.st, one lane = one output
+//     feature) and is the A operand of every MMA (tcgen05.mma [d], [a_tmem], b-desc) -- it costs no shared memory and no
+//     shared-memory bandwidth;
+//   * the activations stream through a 6-stage shared-memory ring as the B operand (K-major swizzle-128B tiles, hi/lo),
+//     loaded with fully coalesced 16-byte accesses;
+//   * the accumulator is feature-major, so an epilogue thread owns ONE output feature: its bias is a register and a warp
+//     store writes 32 consecutive floats of one output row -- one 128-byte wavefront, fully coalesced.
+// History (profiles/r1_gemm_ncu.md): with the activations as the A operand one thread owns one ROW, and both its loads
+// (tcgen05.st wants lane == row) and its stores touch 32 different lines per instruction; ncu showed the LSU data pipe at
+// 80 % with DRAM at 50 % and the MMA warp waiting 40 % of the time for the epilogue to drain the accumulator.
+// TMEM map (512 columns): [0,256) two accumulators (128 tokens each), [256,384) W_hi, [384,512) W_lo.
+constexpr int kWStages = 6;
+constexpr int kWStageBytes = 2 * kTileBytes;                       // X_hi, X_lo
+constexpr size_t kSmemBytesWTmem = (size_t)kWStages * kWStageBytes + 1024 + 256;
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -441,32 +447,66 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
 }
-// one tile row per thread: 32 consecutive floats of row `row` (zero beyond rows_total), four 256-bit loads
-__device__ __forceinline__ void row_load32(const float *__restrict__ src, RowMap map, int row, int rows_total, int k0, float (&v)[32]) {
-    if (row < rows_total) {
-        const float *p = src + map.off(row) + k0;
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// 32 tokens x this thread's feature: C[row(tok0 + j)][col] = r[j] + bias (ReLU); a warp writes 128 contiguous bytes per token
+template <bool kFull>
+__device__ __forceinline__ void store_feature32_impl(float *__restrict__ C, RowMap cmap, int tok0, int n, int col, const uint32_t (&r)[32],
+                                                     float bias, int relu, int lane) {
+    if (cmap.rpb == 0) {
+        float *p = C + (size_t)tok0 * cmap.ld + col;
+        const size_t ld = cmap.ld;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=f"(v[8 * q]), "=f"(v[8 * q + 1]), "=f"(v[8 * q + 2]), "=f"(v[8 * q + 3]), "=f"(v[8 * q + 4]),
-                           "=f"(v[8 * q + 5]), "=f"(v[8 * q + 6]), "=f"(v[8 * q + 7])
-                         : "l"(p + 8 * q));
+        for (int j = 0; j < 32; ++j) {
+            if (kFull || j < n) {
+                float o = __uint_as_float(r[j]) + bias;
+                if (relu) o = fmaxf(o, 0.f);
+                p[j * ld] = o;
+            }
+        }
     } else {
+        // two-level rows: lane j works out the offset of token tok0 + j once (one division), the loop broadcasts it --
+        // independent shuffles instead of a serial wrap-around pointer walk
+        const unsigned long long mine = (unsigned long long)cmap.off(tok0 + min(lane, n - 1));
+        const uint32_t lo = (uint32_t)mine, hi = (uint32_t)(mine >> 32);
+        float *base = C + col;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int j = 0; j < 32; ++j) {
+            const unsigned long long off = ((unsigned long long)__shfl_sync(0xffffffffu, hi, j) << 32) | __shfl_sync(0xffffffffu, lo, j);
+            if (kFull || j < n) {
+                float o = __uint_as_float(r[j]) + bias;
+                if (relu) o = fmaxf(o, 0.f);
+                base[off] = o;
+            }
+        }
     }
 }
+__device__ __forceinline__ void store_feature32(float *__restrict__ C, RowMap cmap, int tok0, int M, int col, const uint32_t (&r)[32],
+                                                float bias, int relu, int lane) {
+    const int n = M - tok0;                                       // valid tokens in this group
+    if (n >= 32) store_feature32_impl<true>(C, cmap, tok0, 32, col, r, bias, relu, lane);
+    else if (n > 0) store_feature32_impl<false>(C, cmap, tok0, n, col, r, bias, relu, lane);
+}
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const float *__restrict__ A, RowMap amap,
+__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const float *__restrict__ A, RowMap amap,
                                                                         const float *__restrict__ B, int ldb,
                                                                         const float *__restrict__ bias, float *__restrict__ C,
-                                                                        RowMap cmap, int M, int N, int K, int relu, bool wide) {
+                                                                        RowMap cmap, int M, int N, int K, int relu) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *bres = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bres + (size_t)kMaxResChunks * 2 * kTileBytes);
-    uint64_t *full = bars, *empty = bars + kAStages, *acc_full = bars + 2 * kAStages, *acc_empty = bars + 2 * kAStages + 2;
-    uint64_t *b_ready = bars + 2 * kAStages + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kAStages + 5);
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kWStages * kWStageBytes);
+    uint64_t *full = bars, *empty = bars + kWStages, *acc_full = bars + 2 * kWStages, *acc_empty = bars + 2 * kWStages + 2;
+    uint64_t *w_ready = bars + 2 * kWStages + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kWStages + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
@@ -474,9 +514,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const fl
     const int n0 = n_blk * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kAStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
-        mbar_init(b_ready, kProducerThreads * kProducerGroups / 32);
+        mbar_init(w_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -487,43 +527,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const fl
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_a0 = tmem_base + 2 * kAccCols;
+    const uint32_t tmem_w_hi = tmem_base + 2 * kAccCols, tmem_w_lo = tmem_w_hi + 128;
 
     if (warp < kMmaWarp) {
         // ===== PRODUCERS =====
         const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
-        for (int kc = g; kc < k_chunks; kc += kProducerGroups)            // resident B block (shared memory), once
-            produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
-                         bres + (size_t)kc * 2 * kTileBytes + kTileBytes, t);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_ready);
-        const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
-        const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
-        const int row_in_tile = (warp & 3) * 32 + lane;                   // == the TMEM lane this thread may write
-        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        // Two register buffers in ping-pong: a buffer is refilled (chunk + 2 rounds ahead) the moment it has been written
-        // to TMEM, so both are in flight except while one is being split -- ~96 KB of loads outstanding per SM.
-        float va[32], vb[32];
-        auto fetch = [&](uint32_t cc, float (&buf)[32]) {
-            if (cc < total_chunks)
-                row_load32(A, amap, (m_first + (int)(cc / k_chunks) * m_step) * BM + row_in_tile, M, (int)(cc % k_chunks) * BK, buf);
-        };
-        auto emit = [&](uint32_t cc, const float (&buf)[32]) {
-            const int stage = cc % kAStages;
-            mbar_wait(&empty[stage], ((cc / kAStages) & 1) ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tcol = tmem_a0 + stage * kAStageCols + lane_addr;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+        if (g == 0) {
+            // the weight block -> TMEM, once: thread = output feature n0 + 32*(warp&3) + lane = its TMEM lane
+            const float *wrow = B + (size_t)(n0 + (warp & 3) * 32 + lane) * ldb;
+            const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+            for (int k0 = 0; k0 < K; k0 += 8) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wrow + k0)), w1 = __ldg(reinterpret_cast<const float4 *>(wrow + k0 + 4));
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
                 float hi[8], lo[8];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) { hi[jj] = tf32_rna(buf[8 * q + jj]); lo[jj] = buf[8 * q + jj] - hi[jj]; }
-                tmem_st8(tcol + 8 * q, hi);
-                tmem_st8(tcol + 32 + 8 * q, lo);
+                for (int q = 0; q < 8; ++q) { hi[q] = tf32_rna(w[q]); lo[q] = w[q] - hi[q]; }
+                tmem_st8(tmem_w_hi + lane_addr + k0, hi);
+                tmem_st8(tmem_w_lo + lane_addr + k0, lo);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(w_ready);
+        }
+        // activation chunks: running index c = tile_iter * k_chunks + kc; this group takes c == g (mod groups).  Two register
+        // buffers in ping-pong: a buffer is refilled (two rounds ahead) as soon as it has been stored to shared memory.
+        const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
+        const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
+        float4 va[8], vb[8];
+        auto fetch = [&](uint32_t cc, float4 (&buf)[8]) {
+            if (cc < total_chunks) tile_load_k(A, amap, (m_first + (int)(cc / k_chunks) * m_step) * BM, M, (int)(cc % k_chunks) * BK, t, buf);
+        };
+        auto emit = [&](uint32_t cc, const float4 (&buf)[8]) {
+            const int stage = cc % kWStages;
+            mbar_wait(&empty[stage], ((cc / kWStages) & 1) ^ 1);
+            unsigned char *st = tiles + (size_t)stage * kWStageBytes;
+            tile_store_k(buf, st, st + kTileBytes, t);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[stage]);
         };
@@ -539,7 +579,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const fl
         }
     } else if (warp == kMmaWarp) {
         // ===== MMA ISSUER =====
-        mbar_wait(b_ready, 0);
+        mbar_wait(w_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t c = 0;
         int it = 0;
         for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
@@ -548,20 +589,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const fl
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + a * kAccCols;
             for (int kc = 0; kc < k_chunks; ++kc, ++c) {
-                const int stage = c % kAStages;
-                mbar_wait(&full[stage], (c / kAStages) & 1);
+                const int stage = c % kWStages;
+                mbar_wait(&full[stage], (c / kWStages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
-                    const uint32_t a_hi = tmem_a0 + stage * kAStageCols, a_lo = a_hi + 32;
-                    const uint32_t bbase = smem_u32(bres + (size_t)kc * 2 * kTileBytes);
-                    const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + kTileBytes);
+                    const uint32_t xbase = smem_u32(tiles + (size_t)stage * kWStageBytes);
+                    const uint64_t x_hi = make_desc(xbase), x_lo = make_desc(xbase + kTileBytes);
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint64_t adv = (uint64_t)(ks * 2);             // 32 bytes along K inside the 128-byte swizzle row
+                        const uint32_t kcol = kc * BK + ks * 8;
                         const uint32_t first = (kc | ks) != 0;
-                        umma_tf32_ts(tmem_d, a_lo + 8 * ks, b_hi + adv, kIdesc, first);
-                        umma_tf32_ts(tmem_d, a_hi + 8 * ks, b_lo + adv, kIdesc, 1u);
-                        umma_tf32_ts(tmem_d, a_hi + 8 * ks, b_hi + adv, kIdesc, 1u);
+                        umma_tf32_ts(tmem_d, tmem_w_lo + kcol, x_hi + adv, kIdesc, first);
+                        umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_lo + adv, kIdesc, 1u);
+                        umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_hi + adv, kIdesc, 1u);
                     }
                     umma_commit(&empty[stage]);
                     if (kc == k_chunks - 1) umma_commit(&acc_full[a]);
@@ -570,35 +611,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_atmem_kernel(const fl
             }
         }
     } else {
-        // ===== EPILOGUE =====
+        // ===== EPILOGUE =====  thread = output feature; accumulator columns = the tile's 128 tokens
         const int q = warp & 3;
+        const int col = n0 + q * 32 + lane;
+        const float bias_f = bias ? __ldg(bias + col) : 0.f;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         int it = 0;
         for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
             const int a = it & 1;
             const int m0 = mb * BM;
             mbar_wait(&acc_full[a], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + q * 32 + lane;
-            float *crow = C + cmap.off(row < M ? row : 0) + n0;
-#pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kAccCols + cb);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(a * kAccCols);
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld32(taddr + 32, rb);
+            store_feature32(C, cmap, m0, M, col, ra, bias_f, relu, lane);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld32(taddr + 64, ra);
+            store_feature32(C, cmap, m0 + 32, M, col, rb, bias_f, relu, lane);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tmem_ld32(taddr + 96, rb);
+            store_feature32(C, cmap, m0 + 64, M, col, ra, bias_f, relu, lane);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // accumulator fully read: hand it back early
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
+            store_feature32(C, cmap, m0 + 96, M, col, rb, bias_f, relu, lane);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -864,17 +904,16 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
         }
         int per_col = dc_sm_count() / n_blocks;                          // CTAs per column block
         if (per_col > m_blocks) per_col = m_blocks;
-        static int use_atmem = -1;                                        // DC_GEMM_ATMEM=0 keeps A in shared memory
-        if (use_atmem < 0) { const char *e = getenv("DC_GEMM_ATMEM"); use_atmem = (e && e[0] == '0') ? 0 : 1; }
-        const bool rows32 = ((uintptr_t)A & 31) == 0 && lda % 8 == 0 && (amap.rpb == 0 || amap.bs % 8 == 0);   // 256-bit row loads
-        if (use_atmem && rows32) {
+        static int use_wtmem = -1;                                        // DC_GEMM_WTMEM=0: weights resident in shared memory instead
+        if (use_wtmem < 0) { const char *e = getenv("DC_GEMM_WTMEM"); use_wtmem = (e && e[0] == '0') ? 0 : 1; }
+        if (use_wtmem) {
             static bool attr_t = false;
             if (!attr_t) {
-                DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesATmem));
+                DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
                 attr_t = true;
             }
-            gemm_tf32x3_atmem_kernel<<<per_col * n_blocks, kThreads, kSmemBytesATmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
-                                                                                                          (int)M, N, K, relu, wide);
+            gemm_tf32x3_wtmem_kernel<<<per_col * n_blocks, kThreads, kSmemBytesWTmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
+                                                                                                          (int)M, N, K, relu);
             DC_LAUNCH_OK();
             return DC_OK;
         }

@@ -44,6 +44,28 @@ def main():
         print("%-28s M=%8d N=%4d K=%4d | ours %.3f ms (%.1f TF/s eff, %.0f GB/s) | cublas fp32 %.3f ms | cublas tf32 %.3f ms | max|diff vs fp32| %.2e"
               % (name, M, N, K, t_ours, flops / t_ours / 1e9, bytes_ / t_ours / 1e6, t_fp32, t_tf32, err))
 
+    # the unit-embedding GEMMs as the encoder issues them: one unit group (16 of 40 rows per token) of [N, 40, 128] in place
+    from dotaclient_b200 import _lib
+    lib = _lib.load()
+    st = _lib.stream_ptr()
+    N_tok, n_u, C = 131072, 16, 128
+    R = N_tok * n_u
+    ue = torch.empty(N_tok, 40, C, device=d)
+    basic = torch.randn(R, C, device=d)
+    w = torch.randn(C, C, device=d) * 0.1
+    bias = torch.randn(C, device=d)
+    off = 6 * C * 4
+    t_c = timeit(lambda: _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, w.data_ptr(), C, bias.data_ptr(),
+                                                              ue.data_ptr() + off, C, n_u, 40 * C, R, C, C, 0, st), "gemm"))
+    t_a = timeit(lambda: _lib.check(lib.dc_gemm_tf32x3_blocked(ue.data_ptr() + off, C, n_u, 40 * C, w.data_ptr(), C, None,
+                                                              basic.data_ptr(), C, 0, 0, R, C, C, 0, st), "gemm"))
+    ref = torch.addmm(bias, basic, w.t()).view(N_tok, n_u, C)
+    _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, w.data_ptr(), C, bias.data_ptr(), ue.data_ptr() + off, C, n_u,
+                                          40 * C, R, C, C, 0, st), "gemm")
+    err = (ue[:, 6:22] - ref).abs().max().item()
+    print("unit group 16/40: C blocked (fwd) %.3f ms | A blocked (dgrad) %.3f ms | %.0f / %.0f GB/s | max|diff| %.2e"
+          % (t_c, t_a, 8.0 * R * C / t_c / 1e6, 8.0 * R * C / t_a / 1e6, err))
+
 
 if __name__ == "__main__":
     main()
