@@ -75,9 +75,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ float tf32_rna(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+    // round-to-nearest, ties away from zero, to 10 mantissa bits: add half an ulp to the magnitude, clear the low 13 bits.
+    // Same result as cvt.rna.tf32.f32 for finite inputs (which ptxas expands to this plus an |v| < inf test); inf stays inf,
+    // a NaN may become inf here but v - hi is then NaN, so it still poisons the product.
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 
 // Row addressing of an operand: plain (row r at r*ld) or two-level (rows grouped in blocks of `rpb` rows that are
@@ -87,8 +88,13 @@ struct RowMap {
     int ld;
     int rpb;          // 0 = plain
     long long bs;
+    unsigned mul;     // r / rpb without a divide: t = umulhi(r, mul); q = (t + ((r - t) >> 1)) >> sh   (exact for all 32-bit r,
+    int sh;           // rpb >= 2; mul = floor(2^32 (2^s - rpb) / rpb) + 1, s = ceil(log2 rpb), sh = s - 1) -- set by make_rowmap
     __device__ __forceinline__ size_t off(int r) const {
-        return rpb > 0 ? (size_t)(r / rpb) * (size_t)bs + (size_t)(r % rpb) * ld : (size_t)r * ld;
+        if (rpb == 0) return (size_t)r * ld;
+        const unsigned n = (unsigned)r, t = __umulhi(n, mul);
+        const unsigned q = (t + ((n - t) >> 1)) >> sh;
+        return (size_t)q * (size_t)bs + (size_t)(n - q * (unsigned)rpb) * ld;
     }
 };
 
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
                 mbar_wait(&empty[stage], phase ^ 1);
                 unsigned char *st = tiles + (size_t)stage * kStageBytes;
                 produce_tile(A, amap, m0, M, kc * BK, st, st + kTileBytes, t);
-                produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
+                produce_tile(B, RowMap{ldb, 0, 0, 0, 0}, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const flo
         // ===== PRODUCERS =====
         const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
         for (int kc = g; kc < k_chunks; kc += kProducerGroups)            // the resident B block, once
-            produce_tile(B, RowMap{ldb, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
+            produce_tile(B, RowMap{ldb, 0, 0, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
                          bres + (size_t)kc * 2 * kTileBytes + kTileBytes, t);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -757,7 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
             tile_store_mn(v, st, st + kTileBytes, t, (want_b && !(i & 1)) ? &cs : nullptr);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
+            if (lane == 0) mbar_arrive(&full[stage]);            // one arrival per warp (128 single arrivals serialise on the barrier)
 #pragma unroll
             for (int q = 0; q < 8; ++q) v[q] = vn[q];
         }
@@ -876,6 +882,20 @@ __global__ void __launch_bounds__(32 * kRedRows) wgrad_reduce_kernel(const float
 
 extern "C" int dc_gemm_tf32x3_supported(int64_t M, int N, int K) { return M > 0 && N > 0 && K > 0 && N % BN == 0 && K % BK == 0; }
 
+// Row map for (ld, rows_per_block, block_stride); one-row blocks are plain rows `block_stride` apart.
+static RowMap make_rowmap(int ld, int64_t rpb, int64_t bs) {
+    RowMap m{ld, 0, 0, 0, 0};
+    if (rpb <= 0) return m;
+    if (rpb == 1) { m.ld = (int)bs; return m; }                    // rowmap_ok: bs < 2^31 in this case
+    m.rpb = (int)rpb;
+    m.bs = (long long)bs;
+    int s = 0;
+    while ((1ull << s) < (unsigned long long)rpb) ++s;            // ceil(log2 rpb) >= 1
+    m.mul = (unsigned)((((unsigned long long)1 << 32) * (((unsigned long long)1 << s) - (unsigned long long)rpb)) / (unsigned long long)rpb + 1);
+    m.sh = s - 1;
+    return m;
+}
+
 static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const float *bias, float *C, RowMap cmap,
                      int64_t M, int N, int K, int relu, dc_stream_t stream) {
     const int lda = amap.ld, ldc = cmap.ld;
@@ -969,11 +989,13 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
     return DC_OK;
 }
 
-static bool rowmap_ok(int64_t rpb, int64_t bs, int ld) { return rpb == 0 || (rpb > 0 && rpb < (1 << 30) && bs >= rpb * (int64_t)ld && bs % 4 == 0); }
+static bool rowmap_ok(int64_t rpb, int64_t bs, int ld) {
+    return rpb == 0 || (rpb > 0 && rpb < (1 << 30) && bs >= rpb * (int64_t)ld && bs % 4 == 0 && (rpb > 1 || bs < (1ll << 31)));
+}
 
 extern "C" int dc_gemm_tf32x3(const float *A, int lda, const float *B, int ldb, const float *bias, float *C, int ldc,
                               int64_t M, int N, int K, int relu, dc_stream_t stream) {
-    return gemm_impl(A, RowMap{lda, 0, 0}, B, ldb, bias, C, RowMap{ldc, 0, 0}, M, N, K, relu, stream);
+    return gemm_impl(A, make_rowmap(lda, 0, 0), B, ldb, bias, C, make_rowmap(ldc, 0, 0), M, N, K, relu, stream);
 }
 
 // Same GEMM with two-level row addressing of A and/or C (rows_per_block = 0 selects the plain form).
@@ -983,19 +1005,19 @@ extern "C" int dc_gemm_tf32x3_blocked(const float *A, int lda, int64_t a_rows_pe
                                       dc_stream_t stream) {
     DC_REQUIRE(rowmap_ok(a_rows_per_block, a_block_stride, lda) && rowmap_ok(c_rows_per_block, c_block_stride, ldc), DC_EINVAL,
                "dc_gemm_tf32x3_blocked: bad block addressing");
-    return gemm_impl(A, RowMap{lda, (int)a_rows_per_block, (long long)a_block_stride}, B, ldb, bias, C,
-                     RowMap{ldc, (int)c_rows_per_block, (long long)c_block_stride}, M, N, K, relu, stream);
+    return gemm_impl(A, make_rowmap(lda, a_rows_per_block, a_block_stride), B, ldb, bias, C,
+                     make_rowmap(ldc, c_rows_per_block, c_block_stride), M, N, K, relu, stream);
 }
 
 extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni, float *dW,
                                     int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream) {
-    return wgrad_impl(dY, RowMap{ldy, 0, 0}, X, RowMap{ldx, 0, 0}, T, No, Ni, dW, ldw, db, accumulate, workspace, stream);
+    return wgrad_impl(dY, make_rowmap(ldy, 0, 0), X, make_rowmap(ldx, 0, 0), T, No, Ni, dW, ldw, db, accumulate, workspace, stream);
 }
 
 extern "C" int dc_gemm_wgrad_tf32x3_blocked(const float *dY, int ldy, int64_t y_rows_per_block, int64_t y_block_stride,
                                             const float *X, int ldx, int64_t T, int No, int Ni, float *dW, int ldw, float *db,
                                             int accumulate, void *workspace, dc_stream_t stream) {
     DC_REQUIRE(rowmap_ok(y_rows_per_block, y_block_stride, ldy), DC_EINVAL, "dc_gemm_wgrad_tf32x3_blocked: bad block addressing");
-    return wgrad_impl(dY, RowMap{ldy, (int)y_rows_per_block, (long long)y_block_stride}, X, RowMap{ldx, 0, 0}, T, No, Ni, dW, ldw,
+    return wgrad_impl(dY, make_rowmap(ldy, y_rows_per_block, y_block_stride), X, make_rowmap(ldx, 0, 0), T, No, Ni, dW, ldw,
                       db, accumulate, workspace, stream);
 }
