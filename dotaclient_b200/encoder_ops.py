@@ -91,22 +91,22 @@ class UnitEncoder(torch.autograd.Function):
         env2 = _f32c(env.detach()).reshape(N, 3)
         w_e, b_e = _f32c(w_e.detach()), _f32c(b_e.detach())
         wait_h2d(env2)
-        with PROFILE.span("env_fwd", 1):
+        with PROFILE.span("env_fwd", 1, 4 * N * (3 + C)):
             _lib.check(lib.dc_env_fwd(env2.data_ptr(), w_e.data_ptr(), b_e.data_ptr(), xcat.data_ptr(), XCAT, N, st), "dc_env_fwd")
         basics = []
         for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
             R = N * n_u
             basic = torch.empty((R, C), dtype=torch.float32, device=dev)
             wait_h2d(units[g])                       # this group's observations may still be in flight over PCIe
-            with PROFILE.span("unit_basic_fwd", 1):
+            with PROFILE.span("unit_basic_fwd", 1, 4 * R * (12 + C)):
                 _lib.check(lib.dc_unit_basic_fwd(units[g].data_ptr(), w_b.data_ptr(), b_b.data_ptr(), basic.data_ptr(), R, st),
                            "dc_unit_basic_fwd")
-            with PROFILE.span("gemm_tf32x3", 1):
+            with PROFILE.span("gemm_tf32x3", 1, 4 * (2 * R * C + C * C)):
                 _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, weights[g].data_ptr(), C, biases[g].data_ptr(),
                                                       _ptr(ue, off * C), C, n_u, TOK, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
             if g < 5:
                 copy = _ptr(xcat, 6 * C) if g == 3 else None
-                with PROFILE.span("unit_max_fwd", 1):
+                with PROFILE.span("unit_max_fwd", 1, N * (4 * n_u * C + 4 * C + C)):
                     _lib.check(lib.dc_unit_max_fwd(_ptr(ue, off * C), TOK, n_u, _ptr(xcat, (g + 1) * C), copy, XCAT,
                                                    argmax[g].data_ptr(), N, st), "dc_unit_max_fwd")
             basics.append(basic)
@@ -139,14 +139,14 @@ class UnitEncoder(torch.autograd.Function):
             d_xm = _ptr(d_xcat, C)
             dw_e = torch.empty((C, 3), dtype=torch.float32, device=dev)
             db_e = torch.empty(C, dtype=torch.float32, device=dev)
-            with PROFILE.span("env_bwd", 2):
+            with PROFILE.span("env_bwd", 2, 4 * N * (2 * C + 3)):
                 _lib.check(lib.dc_env_bwd(d_xcat.data_ptr(), xcat.data_ptr(), XCAT, env2.data_ptr(), dw_e.data_ptr(), db_e.data_ptr(),
                                           N, _env_workspace(dev).data_ptr(), st), "dc_env_bwd")
         if d_ue is None:
             # one dense pass: rank-1 target-unit part (if that head ran) + max-pool routing
             d_ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
             dl, att = pending if pending is not None else (None, None)
-            with PROFILE.span("unit_grad_assemble", 1):
+            with PROFILE.span("unit_grad_assemble", 1, N * (4 * MAX_UNITS * C + 4 * 6 * C + 5 * C + 4 * C + 4 * MAX_UNITS)):
                 _lib.check(lib.dc_unit_grad_assemble(None if dl is None else dl.data_ptr(), None if att is None else att.data_ptr(),
                                                      d_xm, XCAT, argmax.data_ptr(),
                                                      d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
@@ -168,15 +168,15 @@ class UnitEncoder(torch.autograd.Function):
             R = N * n_u
             dw = torch.empty((C, C), dtype=torch.float32, device=dev)
             db = torch.empty(C, dtype=torch.float32, device=dev)
-            with PROFILE.span("gemm_wgrad", 2):        # dW_g = d_emb_g^T basic_g, db_g = colsum(d_emb_g)
+            with PROFILE.span("gemm_wgrad", 2, 4 * (2 * R * C + C * C)):        # dW_g = d_emb_g^T basic_g, db_g = colsum(d_emb_g)
                 _lib.check(lib.dc_gemm_wgrad_tf32x3_blocked(_ptr(d_ue, off * C), C, n_u, TOK, basics[g].data_ptr(), C, R, C, C,
                                                             dw.data_ptr(), C, db.data_ptr(), 0, ws_w.data_ptr(), st),
                            "dc_gemm_wgrad_tf32x3_blocked")
             wt = weights[g].t().contiguous()
-            with PROFILE.span("gemm_tf32x3", 1):       # d_basic_g = d_emb_g W_g
+            with PROFILE.span("gemm_tf32x3", 1, 4 * (2 * R * C + C * C)):       # d_basic_g = d_emb_g W_g
                 _lib.check(lib.dc_gemm_tf32x3_blocked(_ptr(d_ue, off * C), C, n_u, TOK, wt.data_ptr(), C, None,
                                                       d_basic.data_ptr(), C, 0, 0, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
-            with PROFILE.span("unit_basic_bwd", 2):    # through the ReLU into W_b, b_b (shared by the six groups)
+            with PROFILE.span("unit_basic_bwd", 2, 4 * R * (2 * C + 12)):    # through the ReLU into W_b, b_b (shared by the six groups)
                 _lib.check(lib.dc_unit_basic_bwd(d_basic.data_ptr(), basics[g].data_ptr(), units[g].data_ptr(), dw_b.data_ptr(),
                                                  db_b.data_ptr(), R, 1 if g > 0 else 0, ws_b.data_ptr(), st), "dc_unit_basic_bwd")
             dws.append(dw)
@@ -194,7 +194,7 @@ class TargetUnit(torch.autograd.Function):
         N = att.numel() // C
         att2, ue2 = _f32c(att.detach()).reshape(N, C), _f32c(ue.detach()).reshape(N, MAX_UNITS, C)
         logits = torch.empty((N, MAX_UNITS), dtype=torch.float32, device=att.device)
-        with PROFILE.span("target_unit_fwd", 1):
+        with PROFILE.span("target_unit_fwd", 1, 4 * N * (MAX_UNITS * C + C + MAX_UNITS)):
             _lib.check(_lib.load().dc_target_unit_fwd(att2.data_ptr(), ue2.data_ptr(), logits.data_ptr(), N, _lib.stream_ptr()),
                        "dc_target_unit_fwd")
         ctx.save_for_backward(att2, ue2)
@@ -209,7 +209,7 @@ class TargetUnit(torch.autograd.Function):
         dl = _f32c(dlogits).reshape(N, MAX_UNITS)
         d_att = torch.empty_like(att2)
         d_ue = None if ctx.deferred else torch.empty_like(ue2)
-        with PROFILE.span("target_unit_bwd", 1):
+        with PROFILE.span("target_unit_bwd", 1):       # bytes depend on how many tokens used the head (others are skipped)
             _lib.check(_lib.load().dc_target_unit_bwd(dl.data_ptr(), att2.data_ptr(), ue2.data_ptr(), d_att.data_ptr(),
                                                       None if d_ue is None else d_ue.data_ptr(), N, _lib.stream_ptr()),
                        "dc_target_unit_bwd")

@@ -31,10 +31,11 @@ class _Profile:
         self.enabled = enabled
         self.pairs = []
         self.launches = 0
+        self.bytes = {}            # name -> algorithmic HBM bytes of the timed calls (inputs read once + outputs written once)
 
     class _Span:
-        def __init__(self, prof, name, n_launches):
-            self.prof, self.name, self.n = prof, name, n_launches
+        def __init__(self, prof, name, n_launches, nbytes=0):
+            self.prof, self.name, self.n, self.nbytes = prof, name, n_launches, nbytes
 
         def __enter__(self):
             if self.prof.enabled:
@@ -48,10 +49,11 @@ class _Profile:
                 self.e1.record()
                 self.prof.pairs.append((self.name, self.e0, self.e1))
                 self.prof.launches += self.n
+                self.prof.bytes[self.name] = self.prof.bytes.get(self.name, 0) + self.nbytes
             return False
 
-    def span(self, name, n_launches):
-        return _Profile._Span(self, name, n_launches)
+    def span(self, name, n_launches, nbytes=0):
+        return _Profile._Span(self, name, n_launches, nbytes)
 
     def totals(self):
         torch.cuda.synchronize()
@@ -177,7 +179,7 @@ def _rnn_forward_impl(x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
         cbuf[0].copy_(c0.detach().reshape(B, H))
     ws = _rnn_workspace(cell, H, x.device)
     lib = _lib.load()
-    with PROFILE.span("rnn_fwd", 1):
+    with PROFILE.span("rnn_fwd", 1, 4 * S * B * ((4 if cell == "lstm" else 3) + 1) * H):
         _lib.check(lib.dc_rnn_seq_fwd(CELL_ID[cell], gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
                                       ybuf.data_ptr(), cbuf.data_ptr(), B, S, H, ws.data_ptr(), _lib.stream_ptr()),
                    "dc_rnn_seq_fwd")
@@ -232,7 +234,7 @@ class RnnSequence(torch.autograd.Function):
         dc0 = torch.empty((B, H), dtype=torch.float32, device=x2.device) if cell == "lstm" else None
         ws = _rnn_workspace(cell, H, x2.device)
         lib = _lib.load()
-        with PROFILE.span("rnn_bwd", 1):
+        with PROFILE.span("rnn_bwd", 1, 8 * S * B * ((4 if cell == "lstm" else 3) + 1) * H):
             _lib.check(lib.dc_rnn_seq_bwd(CELL_ID[cell], gates.data_ptr(), w_hh.data_ptr(), ybuf.data_ptr(),
                                           cbuf.data_ptr(), dy.data_ptr(), _lib.ptr(dhn), _lib.ptr(dcn), dh0.data_ptr(),
                                           _lib.ptr(dc0), B, S, H, ws.data_ptr(), _lib.stream_ptr()), "dc_rnn_seq_bwd")
@@ -367,7 +369,7 @@ def gemm_tf32x3(a, b, bias=None, relu=False, out=None):
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1
     lib = _lib.load()
-    with PROFILE.span("gemm_tf32x3", 1):
+    with PROFILE.span("gemm_tf32x3", 1, 4 * (M * K + N * K + M * N)):
         _lib.check(lib.dc_gemm_tf32x3(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _lib.ptr(bias), out.data_ptr(),
                                       out.stride(0), M, N, K, 1 if relu else 0, _lib.stream_ptr()), "dc_gemm_tf32x3")
     return out
@@ -456,7 +458,7 @@ def gemm_wgrad_tf32x3(dy, x, want_bias=True, dw_out=None, db_out=None, accumulat
     if ws is None:
         ws = torch.empty(int(lib.dc_gemm_wgrad_workspace_bytes(No, Ni)), dtype=torch.uint8, device=dev)
         _wgrad_ws[key] = ws
-    with PROFILE.span("gemm_wgrad", 2):
+    with PROFILE.span("gemm_wgrad", 2, 4 * (T * No + T * Ni + No * Ni)):
         _lib.check(lib.dc_gemm_wgrad_tf32x3(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), T, No, Ni,
                                             dw_out.data_ptr(), dw_out.stride(0), _lib.ptr(db_out) if want_bias else None,
                                             1 if accumulate else 0, ws.data_ptr(), _lib.stream_ptr()),

@@ -93,3 +93,49 @@ def test_target_unit_forward_backward(lead):
     (out * go.to(d)).sum().backward()
     torch.testing.assert_close(a2.grad.cpu(), att.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(u2.grad.cpu(), ue.grad, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("lead,use_head", [((7,), True), ((3, 5), True), ((130,), True), ((33,), False)])
+def test_unit_encoder_implicit_embedding_gradient(lead, use_head):
+    """The training-path backward: the unit embedding is consumed only by the target-unit head (and the max-pool), so its
+    [N,40,128] gradient is never materialised -- the group GEMMs generate their rows of it (dc_unit_group_dgrad/_wgrad).
+    Compared with plain torch autograd on the CPU (policy.py:99-136,152-153)."""
+    from dotaclient_b200 import encoder_ops
+    g = torch.Generator().manual_seed(17 + sum(lead))
+    env = torch.randn(*lead, 3, generator=g)
+    w_e = (torch.randn(128, 3, generator=g) * 0.5).requires_grad_(True)
+    b_e = (torch.randn(128, generator=g) * 0.1).requires_grad_(True)
+    w_b = (torch.randn(128, 12, generator=g) * 0.3).requires_grad_(True)
+    b_b = (torch.randn(128, generator=g) * 0.1).requires_grad_(True)
+    units = [torch.randn(*lead, n, 12, generator=g) for n in UNITS]
+    weights = [(torch.randn(128, 128, generator=g) * 0.1).requires_grad_(True) for _ in UNITS]
+    biases = [(torch.randn(128, generator=g) * 0.1).requires_grad_(True) for _ in UNITS]
+    att = torch.randn(*lead, 128, generator=g).requires_grad_(True)
+    ue_r, x_r = _reference(env, w_e, b_e, w_b, b_b, units, weights, biases)
+    g_x = torch.randn(x_r.shape, generator=g)
+    loss_r = (x_r * g_x).sum()
+    if use_head:
+        tu_r = torch.matmul(att.unsqueeze(-2), ue_r.transpose(-1, -2)).squeeze(-2)
+        g_tu = torch.randn(tu_r.shape, generator=g)
+        g_tu[..., ::2, :] = 0                              # tokens where the head was not used
+        loss_r = loss_r + (tu_r * g_tu).sum()
+    loss_r.backward()
+
+    d = torch.device("cuda", 0)
+    refs = [w_b, b_b] + weights + biases + [w_e, b_e]
+    params = [t.detach().clone().to(d).requires_grad_(True) for t in refs]
+    att_d = att.detach().to(d).requires_grad_(True)
+    ue, x = encoder_ops.unit_encoder(env.to(d), params[14], params[15], params[0], params[1], [u.to(d) for u in units],
+                                     params[2:8], params[8:14])
+    loss = (x * g_x.to(d)).sum()
+    if use_head:
+        tu = encoder_ops.target_unit(att_d, ue)
+        torch.testing.assert_close(tu.detach().cpu(), tu_r.detach(), rtol=1e-4, atol=1e-4)
+        loss = loss + (tu * g_tu.to(d)).sum()
+    loss.backward()
+    n_tok = ue_r.numel() // (40 * 128)
+    for mine, ref in zip(params, refs):
+        expect = ref.grad if ref.grad is not None else torch.zeros_like(ref)   # e.g. the enemy-tower layer without the head
+        torch.testing.assert_close(mine.grad.cpu(), expect, rtol=2e-4, atol=2e-6 * max(1, n_tok) * 16)
+    if use_head:
+        torch.testing.assert_close(att_d.grad.cpu(), att.grad, rtol=1e-4, atol=1e-4)

@@ -66,6 +66,15 @@ def main():
     print("unit group 16/40: C blocked (fwd) %.3f ms | A blocked (dgrad) %.3f ms | %.0f / %.0f GB/s | max|diff| %.2e"
           % (t_c, t_a, 8.0 * R * C / t_c / 1e6, 8.0 * R * C / t_a / 1e6, err))
 
+    # weight gradient of the same group: dW = d_ue_g^T basic (dY two-level rows, X plain), db = column sums
+    ws = torch.empty(int(lib.dc_gemm_wgrad_workspace_bytes(C, C)), dtype=torch.uint8, device=d)
+    dw, db = torch.empty(C, C, device=d), torch.empty(C, device=d)
+    t_w = timeit(lambda: _lib.check(lib.dc_gemm_wgrad_tf32x3_blocked(ue.data_ptr() + off, C, n_u, 40 * C, basic.data_ptr(), C, R, C, C,
+                                                                    dw.data_ptr(), C, db.data_ptr(), 0, ws.data_ptr(), st), "wgrad"))
+    ref_w = (ue[:, 6:22].reshape(R, C).double().t() @ basic.double()).float()
+    print("unit group 16/40 weight gradient: %.3f ms | %.0f GB/s | max|diff|/max|ref| %.2e"
+          % (t_w, 8.0 * R * C / t_w / 1e6, ((dw - ref_w).abs().max() / ref_w.abs().max()).item()))
+
 
 if __name__ == "__main__":
     main()
