@@ -232,7 +232,7 @@ class ExperienceBatch:
     def nbytes(self):
         return sum(v.numel() * v.element_size() for _, _, v in self.tensors())
 
-    def to(self, device, non_blocking=True):
+    def to(self, device, non_blocking=True, prefetch=False):
         """Host -> device.  From pinned memory the copies are issued on a side stream in the order the step consumes
         them (env, states, unit groups, then the loss inputs) and every tensor gets an event: ``train`` makes the
         compute stream wait per tensor right before first use, so the PCIe transfer of unit group g+1 overlaps the
@@ -241,8 +241,8 @@ class ExperienceBatch:
         overlap = non_blocking and self.advantages.is_pinned()
         compute = torch.cuda.current_stream(device)
         side = _copy_stream(device) if overlap else None
-        if overlap:
-            side.wait_stream(compute)
+        if overlap and not prefetch:
+            side.wait_stream(compute)            # prefetch=True: the copies start now, next to whatever the compute stream is doing
         def priority(item):                      # copy order == order of first use in the step
             holder, k, _ = item
             if holder is self.observations:
@@ -549,6 +549,17 @@ class DotaOptimizer:
         losses = {'loss': res[0], 'policy_loss': res[1], 'entropy_loss': res[2], 'value_loss': res[3]}
         entropies = {k: res[4 + h] for h, k in enumerate(keys)}
         return losses, entropies, {'unclipped': res[_lib.LOSS_SLOTS], 'clipped': res[_lib.LOSS_SLOTS + 1]}
+
+    def prefetch(self, experiences):
+        """Starts the asynchronous upload of a pinned-host ``ExperienceBatch`` on the copy stream and returns the device batch
+        at once (every tensor carries its own ready-event; ``train`` waits per tensor at first use).  Called while the previous
+        step is still computing, it hides the PCIe transfer behind that step (double buffering) -- raw rollout data does not
+        depend on the weights, so an optimizer fed from the experience queue can always upload one batch ahead."""
+        if not isinstance(experiences, ExperienceBatch):
+            experiences = ExperienceBatch.from_sequences(experiences, torch.device("cpu")).pin_memory()
+        if experiences.advantages.is_cuda:
+            return experiences
+        return experiences.to(self.device, prefetch=True)
 
     def mean_gradient_norm(self):
         """Mean per-tensor L2 norm over parameters that got a gradient in the last step (:691-695)."""

@@ -89,3 +89,23 @@ def test_train_accepts_host_pinned_batch(tmp_path):
     np.testing.assert_allclose(float(l1["loss"]), float(l2["loss"]), rtol=1e-6)
     np.testing.assert_allclose(float(g1["unclipped"]), float(g2["unclipped"]), rtol=1e-6)
     torch.testing.assert_close(opt.flat.param, twin.flat.param, rtol=0, atol=1e-7)
+
+
+def test_prefetch_double_buffers_the_upload(tmp_path):
+    """DotaOptimizer.prefetch(): the next batch's H2D copy is issued before the current step is launched; two pipelined
+    steps give the same parameters as two plain train() calls on device-resident batches."""
+    from dotaclient_b200.optimizer import ExperienceBatch
+    opt = _optimizer(tmp_path, uuid.uuid4().int % 100000, checkpoint=False)
+    twin = _optimizer(tmp_path, uuid.uuid4().int % 100000, checkpoint=False)
+    dev = [ExperienceBatch.from_sequences(opt.experiences_from_rollout(make_rollout(32, s)), opt.device) for s in (5, 6)]
+    host = [b.pin_memory() for b in dev]
+    cur = opt.prefetch(host[0])
+    assert cur.advantages.is_cuda and opt.prefetch(cur) is cur          # a device batch passes through
+    nxt = opt.prefetch(host[1])                                         # upload of step 2 in flight while step 1 runs
+    opt.train(cur)
+    l1, _, g1 = opt.train(nxt)
+    twin.train(dev[0])
+    l2, _, g2 = twin.train(dev[1])
+    np.testing.assert_allclose(float(l1["loss"]), float(l2["loss"]), rtol=1e-6)
+    np.testing.assert_allclose(float(g1["unclipped"]), float(g2["unclipped"]), rtol=1e-6)
+    torch.testing.assert_close(opt.flat.param, twin.flat.param, rtol=0, atol=1e-7)
