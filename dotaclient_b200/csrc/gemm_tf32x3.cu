@@ -468,7 +468,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 template <bool kFull>
 __device__ __forceinline__ void store_feature32_impl(float *__restrict__ C, RowMap cmap, int tok0, int n, int col, const uint32_t (&r)[32],
                                                      float bias, int relu, int lane) {
-    if (cmap.rpb == 0) {
+    if (kFull && cmap.ld == 128 && (cmap.rpb == 0 || cmap.rpb == 16)) {
+        // the two layouts nearly all rows of this model go through (a plain [M,128] matrix; 16-unit groups of the
+        // [N,40,128] unit embedding): 32 rows = one or two runs of rows 512 bytes apart -> immediate store offsets,
+        // 2 instructions per row (ncu: the generic path's address arithmetic made the epilogue ~40 % of the kernel's instructions)
+        float *p0, *p1;
+        if (cmap.rpb == 0) {
+            p0 = C + (size_t)tok0 * 128 + col;
+            p1 = p0 + 16 * 128;
+        } else {                                                   // tok0 % 16 == 0 (tiles start on multiples of 128 rows)
+            p0 = C + (size_t)(tok0 >> 4) * (size_t)cmap.bs + col;
+            p1 = p0 + cmap.bs;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float o = __uint_as_float(r[j]) + bias;
+            if (relu) o = fmaxf(o, 0.f);
+            (j < 16 ? p0 : p1)[(j & 15) * 128] = o;
+        }
+    } else if (cmap.rpb == 0) {
         float *p = C + (size_t)tok0 * cmap.ld + col;
         const size_t ld = cmap.ld;
 #pragma unroll
@@ -682,11 +700,25 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
 __device__ __forceinline__ void tile_load_mn(const float *__restrict__ src, RowMap map, int t0, int T, int f0, int t,
                                              float4 (&v)[8]) {
     const int l = t & 31, w = t >> 5;                  // lane -> 4 features, warp -> token (mod 4)
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (map.rpb == 0 || map.rpb >= 4) {
+        // this thread's rows are t0+w, t0+w+4, ...: one offset computation, then a walk (+4 rows, at most one block wrap per step)
+        const float *p = src + map.off(t0 + w) + f0 + 4 * l;
+        const long long step = 4ll * map.ld, wrap = map.rpb > 0 ? map.bs - (long long)map.rpb * map.ld : 0;
+        int rem = 0;
+        if (map.rpb > 0) { const unsigned n = (unsigned)(t0 + w), tq = __umulhi(n, map.mul); rem = (int)(n - ((tq + ((n - tq) >> 1)) >> map.sh) * (unsigned)map.rpb); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = (t0 + w + 4 * i < T) ? __ldg(reinterpret_cast<const float4 *>(p)) : zero4;
+            p += step;
+            if (map.rpb > 0) { rem += 4; if (rem >= map.rpb) { rem -= map.rpb; p += wrap; } }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int tok = w + 4 * i;
-        v[i] = (t0 + tok < T) ? __ldg(reinterpret_cast<const float4 *>(src + map.off(t0 + tok) + f0) + l)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (t0 + tok < T) ? __ldg(reinterpret_cast<const float4 *>(src + map.off(t0 + tok) + f0) + l) : zero4;
     }
 }
 __device__ __forceinline__ void tile_store_mn(const float4 (&v)[8], unsigned char *dst_hi, unsigned char *dst_lo, int t,

@@ -104,13 +104,20 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float *__restrict__ para
     const float coef = s_coef;
     const float beta1 = (float)beta1_d, beta2 = (float)beta2_d, eps = (float)eps_d;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int p = 0; p < n_seg; ++p) {
-        if (!(g[total + p] > 0.f)) continue;             // .grad is None -> Adam skips the tensor
+    // per-tensor scalars once per block (thread p -> tensor p): the float64 pow() calls are ~100 instructions each and were
+    // being repeated by every thread for every tensor (0.10 ms for a 1 MB parameter set)
+    __shared__ float s_bc2[kMaxSeg], s_step[kMaxSeg];
+    for (int p = threadIdx.x; p < n_seg; p += kThreads) {
         // torch computes the bias corrections as Python floats (float64) and folds them into fp32 scalars.
         const int step = steps[p] + 1;
         const double bc1 = 1.0 - pow(beta1_d, (double)step);
-        const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2_d, (double)step));
-        const float step_size = (float)(lr / bc1);
+        s_bc2[p] = (float)sqrt(1.0 - pow(beta2_d, (double)step));
+        s_step[p] = (float)(lr / bc1);
+    }
+    __syncthreads();
+    for (int p = 0; p < n_seg; ++p) {
+        if (!(g[total + p] > 0.f)) continue;             // .grad is None -> Adam skips the tensor
+        const float bc2_sqrt = s_bc2[p], step_size = s_step[p];
         const int64_t lo = seg_lo[p], hi = seg_hi[p];
         for (int64_t i = lo + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < hi; i += stride) {
             const float gi = g[i] * coef;
