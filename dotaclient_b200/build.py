@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libdotaclient_b200.so")
-SOURCES = ["capi.cu", "gae_scan.cu", "ppo_loss.cu", "grad_finish.cu", "rnn_seq.cu", "gemm_tf32x3.cu", "encoder.cu"]
+SOURCES = ["capi.cu", "gae_scan.cu", "ppo_loss.cu", "grad_finish.cu", "rnn_seq.cu", "gemm_tf32x3.cu", "encoder.cu", "actor.cu"]
 
 
 def _nvcc():

@@ -3,6 +3,7 @@
 Every function here requires CUDA tensors and enqueues hand-written sm_100a kernels from
 ``libdotaclient_b200.so`` on torch's current stream.  No CPU path exists: CPU tensors raise.
 """
+import ctypes
 import os
 
 import torch
@@ -464,6 +465,31 @@ def gemm_wgrad_tf32x3(dy, x, want_bias=True, dw_out=None, db_out=None, accumulat
                                             1 if accumulate else 0, ws.data_ptr(), _lib.stream_ptr()),
                    "dc_gemm_wgrad_tf32x3")
     return dw_out, (db_out if want_bias else None)
+
+
+def select_actions(logits, masks, u):
+    """Hierarchical action selection for ``A`` agents in one launch (``policy.py:190-216``).
+
+    ``logits`` / ``masks``: five ``[A, n_h]`` tensors in ``HEAD_KEYS`` order (rows may be strided column slices);
+    ``u``: ``[A, 5]`` uniforms in [0, 1).  Returns ``(chosen [A,5] int32, logp [A,5] fp32)``; ``chosen`` is -1 for the
+    sub-heads the sampled enum does not use.  The index function is pinned to ``oracle.ref_policy.sample_index``."""
+    _need_cuda(u, *logits, *masks)
+    A = u.shape[0]
+    ls, lds, ms = [], [], []
+    for h, (l, m) in enumerate(zip(logits, masks)):
+        l2 = l.reshape(A, HEAD_SIZES[h]).float()
+        if l2.stride(1) != 1:
+            l2 = l2.contiguous()
+        ls.append(l2)
+        lds.append(l2.stride(0))
+        ms.append(m.reshape(A, HEAD_SIZES[h]).contiguous().view(torch.uint8))
+    u2 = _f32c(u).reshape(A, 5)
+    chosen = torch.empty((A, 5), dtype=torch.int32, device=u.device)
+    logp = torch.empty((A, 5), dtype=torch.float32, device=u.device)
+    with PROFILE.span("select_actions", 1):
+        _lib.check(_lib.load().dc_select_actions(_lib.ptr5(ls), (ctypes.c_int64 * 5)(*lds), _lib.ptr5(ms), u2.data_ptr(), A,
+                                                 chosen.data_ptr(), logp.data_ptr(), _lib.stream_ptr()), "dc_select_actions")
+    return chosen, logp
 
 
 # --------------------------------------------------------------------------------------------- packed small heads

@@ -317,6 +317,7 @@ def all_gather(t):                                                        # :193
 # ------------------------------------------------------------------------------------------ optimizer
 class DotaOptimizer:
     MODEL_FILENAME_FMT = "model_%09d.pt"
+    ADAM_FILENAME_FMT = "adam_%09d.state"         # extension: Adam moments of the same iteration (torch.optim.Adam layout)
     BUCKET_NAME = 'dotaservice'
     MODEL_HISTOGRAM_FREQ = 128
     MAX_GRAD_NORM = 0.5
@@ -376,6 +377,11 @@ class DotaOptimizer:
         self.exp_avg_sq = torch.zeros_like(self.flat.param)
         self.adam_steps = torch.zeros(self.flat.n_seg, dtype=torch.int32, device=self.device)
         self.optimizer = _FusedAdamHandle(self)
+        if self.checkpoint and pretrained_model is not None:
+            adam_file = os.path.join(os.path.dirname(pretrained_model), self.ADAM_FILENAME_FMT % (self.iteration_start - 1))
+            if os.path.isfile(adam_file):
+                logger.info('Restoring Adam state from {}'.format(adam_file))
+                self.optimizer.load_state_dict(torch.load(adam_file, map_location='cpu'))
         self._n_actions = torch.zeros(8, dtype=torch.int32, device=self.device)
         self._n_actions[VALUE_SLOT] = 1 if vf_coef > 0 else 0
         self._metrics = torch.zeros(4, dtype=torch.float32, device=self.device)
@@ -413,6 +419,9 @@ class DotaOptimizer:
         if self.checkpoint:
             with open(os.path.join(self.log_dir, self.MODEL_FILENAME_FMT % version), 'wb') as f:
                 f.write(state_dict_b)
+            # extension: the Adam moments next to the weights, in torch.optim.Adam's own format.  The name
+            # does not end in .pt, so the reference's "latest *.pt" scan and its agents never see it.
+            torch.save(self.optimizer.state_dict(), os.path.join(self.log_dir, self.ADAM_FILENAME_FMT % version))
         self.mq.publish_model(msg=state_dict_b, hdr={'version': version})   # :716
 
     # -- experience intake (:314-430) -------------------------------------------------------------
@@ -486,6 +495,70 @@ class DotaOptimizer:
             seq.returns = ret[sl]
             sequences.append(seq)
         return sequences
+
+    def experiences_from_rollouts(self, datas):
+        """All rollouts of an iteration in ONE batched no-grad pass: the rollouts become the batch
+        dimension of a single time-major ``[L_max, R, ...]`` forward (encoder chain, recurrence from the zero state, heads,
+        selected log-probs) and one segmented GAE scan over all of them, instead of ``R`` batch-1 passes whose recurrence
+        runs on a single SM.  Per rollout the result equals ``experiences_from_rollout`` (:328-430): own padding to a
+        multiple of ``seq_len``, own terminal bootstrap, chunks beyond its padded length are not emitted."""
+        S, dev, pol = self.seq_len, self.device, self.policy_base
+        R = len(datas)
+        Ls = [int(d['rewards'].shape[0]) for d in datas]
+        Lps = [(L + S - 1) // S * S for L in Ls]
+        Lmax = max(Lps)
+
+        def batched(group, key, dtype):
+            first = np.asarray(datas[0][group][key])
+            host = np.zeros((Lmax, R) + tuple(first.shape[1:]), dtype=dtype)           # zero padding (:367-382)
+            for i, d in enumerate(datas):
+                host[:Ls[i], i] = np.asarray(d[group][key])
+            return torch.from_numpy(host).to(dev, non_blocking=True)
+
+        obs = {k: batched('observations', k, np.float32) for k in Policy.INPUT_KEYS}
+        masks = {k: batched('masks', k, np.bool_) for k in Policy.OUTPUT_KEYS}
+        actions = {k: batched('actions', k, np.bool_) for k in Policy.OUTPUT_KEYS}
+        rewards_np = np.zeros((R, Lmax, len(REWARD_KEYS)), dtype=np.float32)
+        for i, d in enumerate(datas):
+            rewards_np[i, :Ls[i]] = np.asarray(d['rewards'], dtype=np.float32)
+        with torch.no_grad():
+            x, unit_embedding = pol._encode(obs['env'], [obs[k] for k in Policy.INPUT_KEYS[1:]])
+            r = pol.rnn
+            h0 = torch.zeros((R, pol.hidden_size), dtype=torch.float32, device=dev)
+            c0 = torch.zeros_like(h0) if pol.cell == "lstm" else None
+            ybuf, cbuf = ops.rnn_forward_states(x.contiguous(), r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0,
+                                                h0, c0, pol.cell)
+            logits, values = pol._heads(ybuf[1:], unit_embedding)
+            keys = ops.HEAD_KEYS
+            old_logp = ops.selected_logp([logits[k] for k in keys], [masks[k] for k in keys],
+                                         [actions[k] for k in keys]).view(Lmax, R, 5)        # :387-390
+            # GAE per rollout over ITS padded length: compact the [L_max, R] value grid into back-to-back segments
+            values_lr = values.reshape(Lmax, R)
+            vals_c = torch.cat([values_lr[:Lps[i], i] for i in range(R)])
+            rew_c = torch.from_numpy(np.concatenate([rewards_np[i, :Lps[i]] for i in range(R)])).to(dev)
+            seg = torch.tensor(np.concatenate([[0], np.cumsum(Lps)]), dtype=torch.int64, device=dev)
+            adv_c, ret_c = ops.gae_scan(rew_c, vals_c, seg, gamma=GAMMA, lam=LAMBDA)          # :417-421
+        out = []
+        for i, d in enumerate(datas):
+            base = int(sum(Lps[:i]))
+            sequences = []
+            for j in range(Lps[i] // S):
+                sl = slice(j * S, (j + 1) * S)
+                if pol.cell == "lstm":
+                    hid = (ybuf[j * S, i].reshape(1, 1, -1), cbuf[j * S, i].reshape(1, 1, -1))
+                else:
+                    hid = ybuf[j * S, i].reshape(1, 1, -1)
+                seq = Sequence(game_id=d.get('game_id'), weight_version=d.get('weight_version'), team_id=d.get('team_id'),
+                               observations={k: v[sl, i] for k, v in obs.items()},
+                               actions={k: v[sl, i] for k, v in actions.items()},
+                               masks={k: v[sl, i] for k, v in masks.items()},
+                               values=values_lr[sl, i].reshape(1, S, 1), rewards=rewards_np[i, sl], hidden=hid,
+                               old_logp=old_logp[sl, i])
+                seq.advantages = adv_c[base + j * S: base + (j + 1) * S]
+                seq.returns = ret_c[base + j * S: base + (j + 1) * S]
+                sequences.append(seq)
+            out.append(sequences)
+        return out
 
     @staticmethod
     def list_of_dicts_to_dict_of_lists(x):
@@ -578,15 +651,21 @@ class DotaOptimizer:
         experiences, subrewards, rollout_lens, weight_ages = [], [], [], []
         start_xp = time.time()
         xp_waits = 0
-        while len(experiences) < self.min_seq_per_epoch:                  # :448
-            with torch.no_grad():
-                start_xp_wait = time.time()
-                rollout, rollout_subrewards, rollout_len, weight_version, _ = self.get_rollout()
-                xp_waits += time.time() - start_xp_wait
-                experiences.extend(self.experiences_from_rollout(data=rollout))
+        # The reference pulls and prepares rollouts one at a time until it holds min_seq_per_epoch sequences (:448-466).  The
+        # number of sequences a rollout yields is known from its length alone, so the SAME rollouts are pulled here first and
+        # then prepared together in one batched pass (experiences_from_rollouts).
+        rollouts, n_seq = [], 0
+        while n_seq < self.min_seq_per_epoch:                             # :448
+            start_xp_wait = time.time()
+            rollout, rollout_subrewards, rollout_len, weight_version, _ = self.get_rollout()
+            xp_waits += time.time() - start_xp_wait
+            rollouts.append(rollout)
+            n_seq += (rollout_len + self.seq_len - 1) // self.seq_len
             subrewards.append(rollout_subrewards)
             rollout_lens.append(rollout_len)
             weight_ages.append(it - weight_version)
+        for sequences in self.experiences_from_rollouts(rollouts):
+            experiences.extend(sequences)
         time_xp = time.time() - start_xp
 
         batch = ExperienceBatch.from_sequences(experiences, self.device)  # stacked once, reused by every epoch
@@ -650,12 +729,35 @@ class _FusedAdamHandle:
         self._owner.flat.zero_grad()
 
     def state_dict(self):
+        """``torch.optim.Adam.state_dict()`` layout (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` keyed by the
+        parameter's index in ``named_parameters()`` order; tensors that never received a gradient have no entry, as in torch),
+        so the checkpoint loads into a stock ``torch.optim.Adam`` over the same module and vice versa."""
         o = self._owner
-        return {'exp_avg': o.exp_avg.clone(), 'exp_avg_sq': o.exp_avg_sq.clone(), 'step': o.adam_steps.clone()}
+        steps = o.adam_steps.cpu()
+        state = {}
+        for i, (p, lo, hi) in enumerate(zip(o.flat.params, o.flat.starts, o.flat.ends)):
+            if int(steps[i]) > 0:
+                state[i] = {'step': torch.tensor(float(steps[i])),
+                            'exp_avg': o.exp_avg[lo:hi].view(p.shape).detach().cpu().clone(),
+                            'exp_avg_sq': o.exp_avg_sq[lo:hi].view(p.shape).detach().cpu().clone()}
+        group = dict(self.defaults, lr=o.learning_rate, amsgrad=False, maximize=False, foreach=None, capturable=False,
+                     differentiable=False, fused=None, decoupled_weight_decay=False, params=list(range(o.flat.n_seg)))
+        return {'state': state, 'param_groups': [group]}
 
     def load_state_dict(self, sd):
         o = self._owner
-        o.exp_avg.copy_(sd['exp_avg']); o.exp_avg_sq.copy_(sd['exp_avg_sq']); o.adam_steps.copy_(sd['step'])
+        if 'state' not in sd:                      # round-1 flat layout
+            o.exp_avg.copy_(sd['exp_avg']); o.exp_avg_sq.copy_(sd['exp_avg_sq']); o.adam_steps.copy_(sd['step'])
+            return
+        o.exp_avg.zero_(); o.exp_avg_sq.zero_(); o.adam_steps.zero_()
+        steps = torch.zeros(o.flat.n_seg, dtype=torch.int32)
+        for i, st in sd['state'].items():
+            i = int(i)
+            lo, hi = o.flat.starts[i], o.flat.ends[i]
+            o.exp_avg[lo:hi].copy_(st['exp_avg'].reshape(-1))
+            o.exp_avg_sq[lo:hi].copy_(st['exp_avg_sq'].reshape(-1))
+            steps[i] = int(st['step'])
+        o.adam_steps.copy_(steps)
 
 
 # ------------------------------------------------------------------------------------------ process entry

@@ -224,6 +224,18 @@ class Policy(nn.Module):
         return chosen
 
     @classmethod
+    def select_actions_batched(cls, heads_logits, masks, u=None):
+        """``select_actions`` for a whole pool of agents in ONE kernel launch (``csrc/actor.cu``): ``heads_logits`` /
+        ``masks`` are ``{head: [A, n]}`` CUDA tensors (``[A, 1, n]`` accepted), ``u`` optional ``[A, 5]`` uniforms (drawn with
+        ``torch.rand`` if omitted).  Returns ``({head: int32 [A]} with -1 where the head was not sampled, logp [A, 5])``."""
+        A = heads_logits['enum'].shape[0]
+        dev = heads_logits['enum'].device
+        if u is None:
+            u = torch.rand(A, 5, device=dev)
+        chosen, logp = ops.select_actions([heads_logits[k] for k in ops.HEAD_KEYS], [masks[k] for k in ops.HEAD_KEYS], u.to(dev))
+        return {k: chosen[:, h] for h, k in enumerate(ops.HEAD_KEYS)}, logp
+
+    @classmethod
     def head_masks(cls, selections):
         """All-ones mask for heads that were used, zeros otherwise (``policy.py:218-224``)."""
         return {key: (torch.ones if key in selections else torch.zeros)(1, 1, n, dtype=torch.bool)

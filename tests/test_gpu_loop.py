@@ -1,6 +1,7 @@
 """GPU tests of the iteration driver: in-process broker -> prep -> epochs x train -> checkpoint/publish
 (``optimizer.py:436-579,697-723``), checkpoint format compatibility and resume."""
 import io
+import os
 import pickle
 import uuid
 
@@ -71,6 +72,16 @@ def test_resume_from_latest_checkpoint(tmp_path):
     assert resumed.iteration_start == 3                # optimizer.py:253
     for (k, a), (_, b) in zip(opt.policy_base.state_dict().items(), resumed.policy_base.state_dict().items()):
         assert torch.equal(a, b), k
+    # extension: the Adam moments are checkpointed next to the weights (torch.optim.Adam layout) and restored on resume
+    assert os.path.isfile(os.path.join(str(tmp_path), "adam_000000002.state"))
+    assert torch.equal(opt.exp_avg, resumed.exp_avg) and torch.equal(opt.exp_avg_sq, resumed.exp_avg_sq)
+    assert torch.equal(opt.adam_steps, resumed.adam_steps) and int(resumed.adam_steps.max()) == 4      # 2 iterations x 2 epochs
+    stock = torch.optim.Adam([torch.nn.Parameter(p.detach().cpu().clone()) for p in opt.flat.params], lr=opt.learning_rate)
+    stock.load_state_dict(resumed.optimizer.state_dict())             # a stock torch optimizer accepts it
+    i0 = opt.flat.names.index("affine_pre_rnn.weight")
+    lo, hi = opt.flat.starts[i0], opt.flat.ends[i0]
+    torch.testing.assert_close(stock.state[stock.param_groups[0]['params'][i0]]['exp_avg'].reshape(-1), opt.exp_avg[lo:hi].cpu(),
+                               rtol=0, atol=0)
 
 
 def test_train_accepts_host_pinned_batch(tmp_path):
@@ -109,3 +120,33 @@ def test_prefetch_double_buffers_the_upload(tmp_path):
     np.testing.assert_allclose(float(l1["loss"]), float(l2["loss"]), rtol=1e-6)
     np.testing.assert_allclose(float(g1["unclipped"]), float(g2["unclipped"]), rtol=1e-6)
     torch.testing.assert_close(opt.flat.param, twin.flat.param, rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("cell", ["gru", "lstm"])
+def test_batched_experience_prep_equals_per_rollout_prep(tmp_path, cell):
+    """experiences_from_rollouts (one batched pass over ragged rollouts) == experiences_from_rollout per rollout
+    (optimizer.py:328-430): same chunk count, carried hidden states, old log-probs, values, GAE advantages/returns."""
+    from dotaclient_b200.optimizer import DotaOptimizer
+    opt = DotaOptimizer(rmq_host="loop", rmq_port=uuid.uuid4().int % 100000, epochs=1, min_seq_per_epoch=4, seq_len=8,
+                        learning_rate=1e-4, checkpoint=False, pretrained_model=None, mq_prefetch_count=1, log_dir=str(tmp_path),
+                        entropy_coef=5e-4, vf_coef=0.5, run_local=True, hidden_size=128, cell=cell)
+    datas = [make_rollout(L, 300 + i) for i, L in enumerate((19, 8, 33, 5))]
+    with torch.no_grad():
+        single = [opt.experiences_from_rollout(d) for d in datas]
+        batched = opt.experiences_from_rollouts(datas)
+    assert [len(b) for b in batched] == [len(s) for s in single] == [3, 1, 5, 1]
+    for ss, bs in zip(single, batched):
+        for a, b in zip(ss, bs):
+            for k in a.observations:
+                assert torch.equal(a.observations[k], b.observations[k])
+            for k in a.actions:
+                assert torch.equal(a.actions[k], b.actions[k]) and torch.equal(a.masks[k], b.masks[k])
+            ha = a.hidden if isinstance(a.hidden, tuple) else (a.hidden,)
+            hb = b.hidden if isinstance(b.hidden, tuple) else (b.hidden,)
+            for x, y in zip(ha, hb):
+                torch.testing.assert_close(x, y, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(a.values, b.values, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(a.dense_old_logp(), b.dense_old_logp(), rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(torch.as_tensor(a.advantages), torch.as_tensor(b.advantages), rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(torch.as_tensor(a.returns), torch.as_tensor(b.returns), rtol=1e-5, atol=1e-6)
+            assert np.array_equal(a.rewards, b.rewards)

@@ -420,3 +420,44 @@ def test_cpu_tensors_are_rejected_loudly():
     from dotaclient_b200 import ops
     with pytest.raises(RuntimeError):
         ops.gae_scan(torch.zeros(4), torch.zeros(4), torch.tensor([0, 4]))
+
+
+def test_select_actions_batched_matches_oracle_index_function():
+    """Actor-side hierarchical sampling in one launch (csrc/actor.cu) vs oracle.ref_policy.sample_index (policy.py:190-216):
+    integer parity of the chosen indices for given uniforms, the enum -> sub-head rule, and the chosen log-probabilities."""
+    from oracle.ref_policy import sample_index, masked_softmax
+    from dotaclient_b200.policy import Policy
+    g = torch.Generator().manual_seed(123)
+    A = 300
+    sizes = dict(enum=4, x=9, y=9, target_unit=40, ability=3)
+    logits = {k: torch.randn(A, n, generator=g) * 2.0 for k, n in sizes.items()}
+    masks = {k: torch.rand(A, n, generator=g) < 0.6 for k, n in sizes.items()}
+    for k in masks:
+        masks[k][:, 1 if k == 'target_unit' else 0] = True       # at least one valid entry per row
+    masks['target_unit'][:, 0] = False                            # policy.py:255: unit 0 (self) is never a target
+    masks['enum'][::7] = torch.tensor([True, False, False, False])   # some agents can only no-op
+    u = torch.rand(A, 5, generator=g)
+    d = torch.device("cuda", 0)
+    chosen, logp = Policy.select_actions_batched({k: v.to(d) for k, v in logits.items()}, {k: v.to(d) for k, v in masks.items()},
+                                                 u.to(d))
+    chosen = {k: v.cpu() for k, v in chosen.items()}
+    logp = logp.cpu()
+    follow = {0: (), 1: ('x', 'y'), 2: ('target_unit',), 3: ('ability',)}
+    keys = list(sizes)
+    n_checked = 0
+    for a in range(A):
+        e = sample_index(logits['enum'][a], masks['enum'][a], float(u[a, 0]))
+        assert int(chosen['enum'][a]) == e
+        for h, k in enumerate(keys):
+            if k == 'enum':
+                continue
+            if k in follow[e]:
+                want = sample_index(logits[k][a], masks[k][a], float(u[a, h]))
+                assert int(chosen[k][a]) == want, (a, k)
+                lp = masked_softmax(logits[k][a].view(1, 1, -1), masks[k][a].view(1, 1, -1)).view(-1)[want]
+                np.testing.assert_allclose(float(logp[a, h]), float(lp), rtol=1e-5, atol=1e-6)
+                n_checked += 1
+            else:
+                assert int(chosen[k][a]) == -1
+    assert n_checked > A // 2
+    assert bool((chosen['enum'][::7] == 0).all())
