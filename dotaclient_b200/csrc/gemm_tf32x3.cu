@@ -866,6 +866,182 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__
     }
 }
 
+// ---- weight gradient, dY^T as the A operand in TENSOR MEMORY ------------------------------------------------------------
+// ncu on gemm_wgrad_kernel: splitting BOTH operands through shared memory costs 64 KB of stores + 96 KB of tensor-core reads
+// per 32-token chunk (LSU shared wavefronts 27 % + tensor-core shared wavefronts 35 % + the global loads on the same L1 data
+// path) for 32 KB of HBM data.  Here the dY side never touches shared memory: a producer thread owns ONE output feature o
+// (= its TMEM lane), loads dY[t][o] for the chunk's 32 tokens -- a warp load is 32 consecutive features of one token, 128
+// coalesced bytes -- splits hi/lo in registers and writes 32 + 32 TMEM columns with tcgen05.st; the MMAs take A from TMEM
+// (tcgen05.mma [d], [a], b-desc).  Only X goes through the (now 6-stage) shared-memory ring as the MN-major B operand.
+// Roles: warps 0-7 two A-producer groups (quadrant = warp & 3; also the epilogue), warps 8-15 two B-producer groups,
+// warp 16 MMA issuer.  TMEM: [0,128) accumulator, [128,384) four A stages of 64 columns.
+constexpr int kGAStages = 4, kGBStages = 6;
+constexpr int kGMmaWarp = 16;
+constexpr int kThreadsG = (kGMmaWarp + 1) * 32;                     // 544
+constexpr size_t kSmemBytesWgradA = (size_t)kGBStages * 2 * kTileBytes + 1024 + 256 + 2 * 128 * sizeof(float);
+constexpr uint32_t kIdescBMN = kIdesc | (1u << 16);                  // A: TMEM (K-major by construction), B: MN-major shared memory
+
+__global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const float *__restrict__ dY, RowMap ymap,
+                                                                        const float *__restrict__ X, RowMap xmap, int T, int No,
+                                                                        int Ni, int nsplit, float *__restrict__ part_w,
+                                                                        float *__restrict__ part_b) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kGBStages * 2 * kTileBytes);
+    uint64_t *a_full = bars, *a_empty = bars + kGAStages, *b_full = bars + 2 * kGAStages, *b_empty = b_full + kGBStages;
+    uint64_t *acc_full = b_empty + kGBStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    float *colsum_s = reinterpret_cast<float *>(acc_full + 2);              // [2 A groups][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
+    const int tile = blockIdx.x % tiles_mn, split = blockIdx.x / tiles_mn;
+    const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+    const int chunks_total = (T + BK - 1) / BK;
+    const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kGBStages; ++s) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kGMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a0 = tmem_base + kAccCols;
+
+    if (warp < 8) {
+        // ===== A PRODUCERS (dY^T -> TMEM) =====  group ga takes chunks j == ga (mod 2); thread = output feature
+        const int ga = warp >> 2, q = warp & 3;
+        const int o = m0 + q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const bool want_b = part_b != nullptr && n0 == 0;
+        float cs = 0.f;
+        float va[32], vb[32];
+        auto fetch = [&](int j, float (&buf)[32]) {
+            if (j >= my_chunks) return;
+            const int t0 = (split + j * nsplit) * BK;
+            // rows t0 .. t0+31 of dY: offset of the first, then a walk (+1 row, block wrap for two-level maps)
+            const float *p = dY + ymap.off(t0) + o;
+            int rem = 0;
+            if (ymap.rpb > 0) { const unsigned n = (unsigned)t0, tq = __umulhi(n, ymap.mul); rem = (int)(n - ((tq + ((n - tq) >> 1)) >> ymap.sh) * (unsigned)ymap.rpb); }
+            const long long wrap = ymap.rpb > 0 ? ymap.bs - (long long)ymap.rpb * ymap.ld : 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                buf[i] = (t0 + i < T) ? __ldg(p) : 0.f;
+                p += ymap.ld;
+                if (ymap.rpb > 0 && ++rem == ymap.rpb) { rem = 0; p += wrap; }
+            }
+        };
+        auto emit = [&](int j, const float (&buf)[32]) {
+            const int stage = j % kGAStages;
+            mbar_wait(&a_empty[stage], ((j / kGAStages) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tcol = tmem_a0 + stage * 64 + lane_addr;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(buf[8 * k8 + e]); lo[e] = buf[8 * k8 + e] - hi[e]; cs += buf[8 * k8 + e]; }
+                tmem_st8(tcol + 8 * k8, hi);
+                tmem_st8(tcol + 32 + 8 * k8, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[stage]);
+        };
+        fetch(ga, va);
+        fetch(ga + 2, vb);
+        for (int j = ga; j < my_chunks; j += 4) {
+            emit(j, va);
+            fetch(j + 4, va);
+            if (j + 2 < my_chunks) {
+                emit(j + 2, vb);
+                fetch(j + 6, vb);
+            }
+        }
+        if (want_b) colsum_s[ga * 128 + q * 32 + lane] = cs;
+        if (ga == 0) {
+            // ===== EPILOGUE: TMEM partial -> workspace [split][tile][128][128] =====
+            float *prow = part_w + (((size_t)split * tiles_mn + tile) * BM + q * 32 + lane) * BN;
+            if (my_chunks > 0) {
+                mbar_wait(acc_full, 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+#pragma unroll 1
+            for (int cb = 0; cb < BN; cb += 32) {
+                uint32_t r[32];
+                if (my_chunks > 0) {
+                    tmem_ld32(tmem_base + lane_addr + (uint32_t)cb, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) r[jj] = 0u;
+                }
+                store_row32(prow + cb, r, nullptr, 0, true);                  // workspace rows are 512-byte aligned
+            }
+        }
+    } else if (warp < kGMmaWarp) {
+        // ===== B PRODUCERS (X -> MN-major shared-memory tiles) =====  group gb takes chunks j == gb (mod 2)
+        const int gb = (warp - 8) >> 2, t = threadIdx.x & (kProducerThreads - 1);
+        float4 v[8], vn[8];
+        int j = gb;
+        if (j < my_chunks) tile_load_mn(X, xmap, (split + j * nsplit) * BK, T, n0, t, v);
+        for (; j < my_chunks; j += 2) {
+            if (j + 2 < my_chunks) tile_load_mn(X, xmap, (split + (j + 2) * nsplit) * BK, T, n0, t, vn);
+            const int stage = j % kGBStages;
+            mbar_wait(&b_empty[stage], ((j / kGBStages) & 1) ^ 1);
+            unsigned char *st = tiles + (size_t)stage * 2 * kTileBytes;
+            tile_store_mn(v, st, st + kTileBytes, t, nullptr);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[stage]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = vn[e];
+        }
+    } else {
+        // ===== MMA ISSUER =====
+        for (int j = 0; j < my_chunks; ++j) {
+            const int sa = j % kGAStages, sb = j % kGBStages;
+            mbar_wait(&a_full[sa], (j / kGAStages) & 1);
+            mbar_wait(&b_full[sb], (j / kGBStages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t base = smem_u32(tiles + (size_t)sb * 2 * kTileBytes);
+                const uint32_t a_hi0 = tmem_a0 + sa * 64, a_lo0 = a_hi0 + 32;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {                          // 8 tokens = two 4-token groups per MMA
+                    const uint32_t adv = ks * 2 * kKGroupBytes;
+                    const uint64_t b_hi = make_desc_mn(base + adv), b_lo = make_desc_mn(base + kTileBytes + adv);
+                    const uint32_t first = (j | ks) != 0;
+                    umma_tf32_ts(tmem_base, a_lo0 + 8 * ks, b_hi, kIdescBMN, first);
+                    umma_tf32_ts(tmem_base, a_hi0 + 8 * ks, b_lo, kIdescBMN, 1u);
+                    umma_tf32_ts(tmem_base, a_hi0 + 8 * ks, b_hi, kIdescBMN, 1u);
+                }
+                umma_commit(&a_empty[sa]);
+                umma_commit(&b_empty[sb]);
+                if (j == my_chunks - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (part_b != nullptr && n0 == 0 && threadIdx.x < 128)           // column sums of this CTA's share of dY (fixed order)
+        part_b[(size_t)split * No + m0 + threadIdx.x] = colsum_s[threadIdx.x] + colsum_s[128 + threadIdx.x];
+    if (warp == kGMmaWarp) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
 // dW[o][i] (+)= sum_split part_w[split][tile][o%128][i%128];  db[o] (+)= sum_split part_b[split][o].
 // One float4 of [dW | db] per thread column, the splits dealt to 8 thread rows (s = y, y+8, ...) whose partial sums are
 // then added in row order: a fixed summation tree (deterministic) with 8x the loads in flight of a serial loop.
@@ -1013,7 +1189,19 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
     float *part_w = reinterpret_cast<float *>(workspace);
     float *part_b = db ? part_w + (size_t)nsplit * No * Ni : nullptr;
     cudaStream_t st = dc_cu_stream(stream);
-    gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
+    static int use_atmem = -1;                                        // DC_WGRAD_ATMEM=0: both operands through shared memory
+    if (use_atmem < 0) { const char *e = getenv("DC_WGRAD_ATMEM"); use_atmem = (e && e[0] == '0') ? 0 : 1; }
+    if (use_atmem) {
+        static bool attr_a = false;
+        if (!attr_a) {
+            DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
+            attr_a = true;
+        }
+        gemm_wgrad_atmem_kernel<<<tiles_mn * nsplit, kThreadsG, kSmemBytesWgradA, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w,
+                                                                                    part_b);
+    } else {
+        gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
+    }
     DC_LAUNCH_OK();
     const int total4 = No * Ni / 4 + (db ? No / 4 : 0);
     wgrad_reduce_kernel<<<(total4 + 31) / 32, 32 * kRedRows, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);
