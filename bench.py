@@ -249,6 +249,8 @@ def run_stream(args, cfg):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to STDOUT; stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl")
     epochs = 4
     opt = DotaOptimizer(rmq_host="stream", rmq_port=rank, epochs=epochs, min_seq_per_epoch=cfg["batch"], seq_len=cfg["seq_len"],
@@ -322,6 +324,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to STDOUT; stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl")
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     dev = torch.device("cuda", local_rank)
