@@ -81,6 +81,26 @@ class FlatParameterSpace:
         self.grad_full.zero_()
         self.rebind()
 
+    def zero_grad_detached(self):
+        """Zeroes the flat gradient buffer and DETACHES every ``.grad`` (sets it to None): autograd then hands each parameter
+        its gradient tensor as is instead of launching one ``grad += new`` kernel per parameter (34 small launches per step);
+        ``gather_grads`` moves them into the flat buffer with one multi-tensor copy and re-attaches the views."""
+        self.grad_full.zero_()
+        for p in self.params:
+            p.grad = None
+
+    def gather_grads(self):
+        dsts, srcs = [], []
+        for p, lo, hi in zip(self.params, self.starts, self.ends):
+            g = p.grad
+            view = self.grad[lo:hi].view(p.shape)
+            if g is not None and g.data_ptr() != view.data_ptr():
+                dsts.append(view)
+                srcs.append(g.detach())
+            p.grad = view
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
+
     def grad_of(self, name):
         i = self.names.index(name)
         return self.grad[self.starts[i]:self.ends[i]].view(self.params[i].shape)

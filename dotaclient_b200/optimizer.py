@@ -576,7 +576,7 @@ class DotaOptimizer:
             batch = ExperienceBatch.from_sequences(experiences, self.device)
         keys = ops.HEAD_KEYS
         t_enter = time.perf_counter()
-        self.flat.zero_grad()                                             # :671
+        self.flat.zero_grad_detached()                                    # :671 (grads gathered into the flat buffer below)
         hidden = (batch.h0, batch.c0) if self.policy_base.cell == "lstm" else batch.h0
         ddp = self.policy if isinstance(self.policy, DistributedDataParallelSparseParamCPU) else None
         if ddp is not None:
@@ -599,6 +599,7 @@ class DotaOptimizer:
             self._n_actions[:5].copy_(n_actions)
             torch.autograd.backward([logits[k] for k in keys] + [values],
                                     [g.view_as(logits[k]) for g, k in zip(dlogits, keys)] + [dvalue.view_as(values)])  # :672
+        self.flat.gather_grads()
         # distributed.py:29-57 -> flags + ONE all-reduce; divide fused into the finish kernel
         ops.grad_flags(self.flat.grad_full, self.flat.total, self.flat.seg_head, self._n_actions)
         if ddp is not None:
