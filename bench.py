@@ -188,7 +188,7 @@ def run_reference_arm(args, cfg):
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "one host: N reference ranks would share these cores, so the per-rank-batch rate does not grow with N",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(cfg, n_gpus, where):
@@ -249,8 +249,6 @@ def run_stream(args, cfg):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to STDOUT; stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl")
     epochs = 4
     opt = DotaOptimizer(rmq_host="stream", rmq_port=rank, epochs=epochs, min_seq_per_epoch=cfg["batch"], seq_len=cfg["seq_len"],
@@ -292,19 +290,35 @@ def run_stream(args, cfg):
     stop.set()
     if rank == 0:
         sec = float(el.item())
-        print(json.dumps({"metric": "optimizer_steps_per_sec", "value": world * args.steps * epochs / sec, "unit": "steps/s",
+        emit({"metric": "optimizer_steps_per_sec", "value": world * args.steps * epochs / sec, "unit": "steps/s",
                           "n_gpus": world, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": 1000 * sec / (args.steps * epochs),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "env_steps_per_sec": world * env_steps / sec,
                           "config": {"workload": "BASELINE configs[4]: 40-agent replay stream, in-process broker, reference defaults "
                                                  "(>=1024 seqs x 16 per iteration, 4 epochs, hidden 256 GRU); 'step' = one train() call "
                                                  "including its share of experience prep", "agents": agents * world,
-                                     "parallelism": "dp%d" % world}}))
+                                     "parallelism": "dp%d" % world}})
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of this run, on the process's real stdout."""
+    out = os.fdopen(os.dup(_REAL_STDOUT), "w") if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there at the first
+    # collective) are sent to stderr for the whole run; emit() writes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     cfg = resolve_config(args)
     if cfg.get("stream"):
@@ -324,8 +338,6 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to STDOUT; stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl")
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     dev = torch.device("cuda", local_rank)
@@ -473,7 +485,7 @@ def main():
         log("timing the CPU baseline (oracle port)")
         v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=20.0)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
