@@ -118,6 +118,30 @@ def test_autograd_accumulates_into_flat_views():
         assert p.grad.data_ptr() == flat.grad[lo:].data_ptr()
 
 
+def test_detached_grads_gathered_into_flat_buffer():
+    """train()'s gradient path: .grad detached before backward (autograd hands tensors over without an accumulate kernel per
+    parameter), then one multi-tensor copy into the flat buffer; parameters without a gradient stay zero and every .grad
+    is a flat view again afterwards."""
+    m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 1), torch.nn.Linear(2, 2))     # the last layer is unused
+    twin = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 1), torch.nn.Linear(2, 2))
+    twin.load_state_dict(m.state_dict())
+    flat = FlatParameterSpace(m)
+    flat.grad.fill_(7.0)                                       # stale contents must not survive
+    flat.zero_grad_detached()
+    assert all(p.grad is None for p in m.parameters()) and float(flat.grad_full.abs().sum()) == 0.0
+    x = torch.arange(8.0).reshape(2, 4)
+    m[1](m[0](x)).sum().backward()
+    twin[1](twin[0](x)).sum().backward()
+    assert m[0].weight.grad.data_ptr() != flat.grad_of("0.weight").data_ptr()      # handed over, not accumulated in place
+    flat.gather_grads()
+    for (name, p), q in zip(m.named_parameters(), twin.parameters()):
+        assert p.grad.data_ptr() == flat.grad_of(name).data_ptr()
+        expect = q.grad if q.grad is not None else torch.zeros_like(q)
+        assert torch.equal(p.grad, expect), name
+    flat.gather_grads()                                        # idempotent when the views are already attached
+    assert torch.equal(m[0].weight.grad, twin[0].weight.grad)
+
+
 # ------------------------------------------------------------------------------------------------ DDP over gloo
 def _ddp_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
