@@ -9,19 +9,27 @@
 //   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, three tcgen05.mma.kind::tf32 per k-step into one fp32
 //   TMEM accumulator.  The dropped a_lo*b_lo term and the truncation of the lo parts are O(2^-22).
 //
-// Structure (one CTA per SM, persistent over 128x128 output tiles, 13 warps):
-//   warps 0-7  PRODUCERS (two groups of 4 warps taking alternate k-chunks, so that the global-load latency of one
-//              chunk overlaps the split arithmetic of the other): coalesced 16-byte global loads of a [128 x 32] fp32 chunk of A and of B, hi/lo split
-//              on the CUDA cores, stores into the canonical K-major SWIZZLE_128B shared-memory layout
-//              (4 tiles of 16 KB per stage: A_hi, A_lo, B_hi, B_lo), fence.proxy.async, mbarrier arrive.
-//              (TMA cannot do this step: the split is arithmetic, so the data passes through registers anyway.)
-//   warp  8    MMA ISSUER: one elected lane issues 12 tcgen05.mma (4 k-steps x 3 products) per stage from
-//              shared-memory descriptors, tcgen05.commit releases the stage / publishes the accumulator.
-//   warps 9-12 EPILOGUE: tcgen05.ld 32x32b (one TMEM lane = one output row per thread), + bias, ReLU, 16-byte
-//              global stores.  Two TMEM accumulator buffers (2 x 128 columns) overlap the epilogue of tile i
-//              with the main loop of tile i+1.
-// Tensor-pipe work: 2*M*N*K*3 flops; HBM: 4*(M*K + N*K + M*N) bytes.  For the K=128 GEMMs of this model the
-// kernel is HBM-bound even with the 3x flops.
+// Four kernels share the building blocks below (one persistent CTA per SM, warp-specialised, 17 warps):
+//   gemm_tf32x3_kernel        any K: A and B both stream through a 3-stage shared-memory ring (4 tiles of 16 KB per stage:
+//                             A_hi, A_lo, B_hi, B_lo); used for K > 128 (affine_pre_rnn, the i2h data gradient).
+//   gemm_tf32x3_wtmem_kernel  K <= 128 (nearly every layer of this model): the TRANSPOSED product with the weight block
+//                             resident in tensor memory as the A operand; activations through a 6-stage ring; an epilogue
+//                             thread owns one output feature.  See the comment above the kernel.
+//   gemm_tf32x3_bres_kernel   K <= 128 fallback (DC_GEMM_WTMEM=0): weight block resident in shared memory.
+//   gemm_wgrad_atmem_kernel   weight gradient dW = dY^T X (split-K), dY^T fed to the MMAs from tensor memory
+//                             (gemm_wgrad_kernel: both operands through shared memory, DC_WGRAD_ATMEM=0).
+// Roles in every kernel:
+//   PRODUCER warps (groups of 4 taking alternate k-chunks, so the global-load latency of one chunk overlaps the split
+//              arithmetic of another): coalesced global loads of a [128 x 32] fp32 chunk, hi/lo split on the CUDA cores,
+//              stores into the canonical SWIZZLE_128B shared-memory layout (or tcgen05.st into TMEM), fence.proxy.async,
+//              one elected mbarrier arrive per warp.  (TMA cannot do this step: the split is arithmetic, so the data passes
+//              through registers anyway.)
+//   MMA ISSUER (one warp): an elected lane issues 12 tcgen05.mma (4 k-steps x 3 products) per 32-wide k-chunk from
+//              shared-memory descriptors / TMEM addresses; tcgen05.commit releases the stage / publishes the accumulator.
+//   EPILOGUE   (4 warps): tcgen05.ld 32x32b, + bias, ReLU, global stores.  Two TMEM accumulator buffers (2 x 128 columns)
+//              overlap the epilogue of tile i with the main loop of tile i+1.
+// Tensor-pipe work: 2*M*N*K*3 flops; HBM: 4*(M*K + N*K + M*N) bytes.  For the K=128 GEMMs of this model the kernels are
+// HBM-bound even with the 3x flops (measured: 5.2-5.5 TB/s on the 2M x 128 x 128 layers).
 #include "dc_common.cuh"
 #include <cstdlib>
 
