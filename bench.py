@@ -316,9 +316,13 @@ def main():
     # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there at the first
     # collective) are sent to stderr for the whole run; emit() writes to the saved descriptor.
     global _REAL_STDOUT
-    sys.stdout.flush()
-    _REAL_STDOUT = os.dup(1)
-    os.dup2(2, 1)
+    try:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        _REAL_STDOUT = saved
+    except OSError:                                  # no usable stderr: keep the plain stdout
+        _REAL_STDOUT = None
     args = parse_args()
     cfg = resolve_config(args)
     if cfg.get("stream"):
