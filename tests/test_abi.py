@@ -61,3 +61,28 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "reference_shim" not in text, f
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: nothing under dotaclient_b200/ (nor the C sources) may import, load or mention it, and
+    nothing shipped may read /root/reference at run time (it does not exist on the GPU box)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "dotaclient_b200")
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        if os.path.basename(d) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(d, f), encoding="utf-8", errors="replace").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "oracle/" in text and f.endswith(".py") and "import" in text and \
+                    re.search(r"(CDLL|open)\([^)]*oracle", text):
+                offenders.append(os.path.join(d, f))
+            if "/root/reference" in text:
+                offenders.append(os.path.join(d, f) + " (reads /root/reference)")
+    assert not offenders, offenders
+    for name in ("bench.py", "__graft_entry__.py"):
+        text = open(os.path.join(root, name), encoding="utf-8").read()
+        assert "/root/reference" not in text, name
