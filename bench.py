@@ -160,6 +160,7 @@ def run_reference_arm(args, cfg):
     torch.manual_seed(7)
     opt = RO.RefOptimizer(RefPolicy(H, cell), seq_len=S)
     seqs = opt.experiences_from_rollout(make_rollout(S, 7))
+    opt.train(seqs)                                        # untimed: thread pool / allocator warm-up must not end the sizing loop
     b = 1
     while True:                                            # grow the sample until one step takes >= 1 s (cap 32 sequences)
         t0 = time.perf_counter()
