@@ -3,14 +3,17 @@
 // The 128x128 unit-embedding GEMMs run on the tensor cores (gemm_tf32x3.cu); everything around them is
 // bandwidth work on ~20 KB/token of activations and is written here so that each tensor crosses HBM once:
 //
-//   unit_basic_fwd   relu(units W_b^T + b_b)            [R,12] -> [R,128]     (K = 12: not a tensor-core shape)
-//   unit_basic_bwd   dW_b, db_b from d_basic, the ReLU mask and the raw units  (the inputs need no gradient)
-//   unit_max_fwd     max over the units of a group + argmax (uint8), written straight into the concatenated
-//                    pre-rnn input row (no torch.cat), policy.py:102-136
-//   unit_max_bwd     routes d(max) to the arg-max unit IN PLACE in d(unit embedding): 768 read-modify-writes per
-//                    token instead of three dense [N,40,128] passes (zeros + scatter + add)
-//   target_unit_fwd  logits[n,u] = <attention[n,:], unit_embedding[n,u,:]>      (policy.py:152-153)
-//   target_unit_bwd  d_attention and the rank-1 d(unit embedding)
+//   env_fwd / env_bwd   relu(env W_e^T + b_e), 3 -> 128, written into / read from columns [0,128) of the concatenated
+//                       [N, 896] pre-rnn input row (no torch.cat), policy.py:55,97
+//   unit_basic_fwd      relu(units W_b^T + b_b)            [R,12] -> [R,128]     (K = 12: not a tensor-core shape)
+//   unit_basic_bwd      dW_b, db_b from d_basic, the ReLU mask and the raw units  (the inputs need no gradient); the three
+//                       input streams come through a 3-stage ring of 1-D TMA bulk copies
+//   unit_max_fwd        max over the units of a group + argmax (uint8), written straight into the concatenated
+//                       pre-rnn input row, policy.py:102-136
+//   unit_grad_assemble  d(unit embedding) in ONE dense pass: rank-1 target-unit part + max-pool routing to the arg-max unit
+//                       (the training path; unit_max_bwd is the in-place scatter used when an explicit gradient arrives)
+//   target_unit_fwd     logits[n,u] = <attention[n,:], unit_embedding[n,u,:]>      (policy.py:152-153)
+//   target_unit_bwd     d_attention (and, outside the training path, the rank-1 d(unit embedding))
 //
 // Thread mapping everywhere: one warp per row of 128 channels, lane l owns channels 4l..4l+3 -> every global access
 // is a fully coalesced 512-byte row segment (16 bytes per lane).
