@@ -211,3 +211,30 @@ def test_nrank_oracle_matches_reference_under_gloo(tmp_path):
             np.testing.assert_allclose(float(g["clipped"]), ref["recs"][ep][2], rtol=1e-6)
         for k, v in opts[r].policy_base.state_dict().items():
             torch.testing.assert_close(v, ref["sd"][k], rtol=0, atol=1e-7, msg=lambda m: k + m)
+
+
+def test_target_unit_head_is_linear_in_the_unit_embedding():
+    """Algebra behind DESIGN.md section 9 item 1 (checked on the CPU so the round-2 kernels have a pinned target):
+    logits[n,u] = <att[n], W_g basic[n,u] + b_g> = <att[n] W_g, basic[n,u]> + <att[n], b_g>   (policy.py:101-131,152-153)
+    and d_att[n] = W_g (sum_u dl[n,u] basic[n,u]) + (sum_u dl[n,u]) b_g -- neither needs the [N,40,128] embedding."""
+    g = torch.Generator().manual_seed(5)
+    N, units = 37, (1, 5, 16, 16, 1, 1)
+    att = torch.randn(N, 128, generator=g, dtype=torch.float64).requires_grad_(True)
+    basics = [torch.relu(torch.randn(N, n, 128, generator=g, dtype=torch.float64)) for n in units]
+    Ws = [torch.randn(128, 128, generator=g, dtype=torch.float64) * 0.1 for _ in units]
+    bs = [torch.randn(128, generator=g, dtype=torch.float64) * 0.1 for _ in units]
+    ue = torch.cat([b @ W.t() + bias for b, W, bias in zip(basics, Ws, bs)], dim=1)          # [N, 40, 128]
+    ref = torch.matmul(att.unsqueeze(-2), ue.transpose(-1, -2)).squeeze(-2)                    # policy.py:152-153
+    dl = torch.randn(ref.shape, generator=g, dtype=torch.float64)
+    (ref * dl).sum().backward()
+    with torch.no_grad():
+        logits, d_att, off = [], torch.zeros_like(att), 0
+        for b, W, bias, n in zip(basics, Ws, bs, units):
+            q = att @ W                                   # [N,128]: ONE small GEMM over tokens instead of n_u x as many rows
+            c = att @ bias                                # [N]
+            logits.append(torch.einsum("nc,nuc->nu", q, b) + c[:, None])
+            P = torch.einsum("nu,nuc->nc", dl[:, off:off + n], b)
+            d_att += P @ W.t() + dl[:, off:off + n].sum(1, keepdim=True) * bias
+            off += n
+        torch.testing.assert_close(torch.cat(logits, dim=1), ref.detach(), rtol=1e-10, atol=1e-10)
+        torch.testing.assert_close(d_att, att.grad, rtol=1e-10, atol=1e-10)
