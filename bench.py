@@ -53,6 +53,7 @@ def parse_args():
     p.add_argument("--cuda-profiler", action="store_true",
                    help="bracket the HBM-resident timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     p.add_argument("--skip-e2e", action="store_true", help="(profiling only) skip the host-buffer timed region")
+    p.add_argument("--no-extra", action="store_true", help="skip the extra_configs block (C1/C3/C4 per-GPU shapes, 3 steps each)")
     return p.parse_args()
 
 
@@ -141,7 +142,7 @@ def cpu_reference_steps_per_sec(cfg, budget_s=20.0, threads=None):
     full = sample_steps_per_s * b / B
     sample = "oracle port of optimizer.py:581-689, batch %d x seq %d (hidden %d, %s), %d steps in %.1f s on %d threads; " \
              "scaled x%d/%d to batch %d" % (b, S, H, cell, n, el, cores, b, B, B)
-    return full, cores, sample
+    return full, cores, sample, b
 
 
 def run_reference_arm(args, cfg):
@@ -186,9 +187,11 @@ def run_reference_arm(args, cfg):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(cfg, args.gpus, "cpu"),
-        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "sample_batch": b, "scale_factor": b / float(B)},
         "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "one host: N reference ranks would share these cores, so the per-rank-batch rate does not grow with N",
+        "note": "ONE CPU process on this host's cores (rank 0 only), also when --gpus N > 1: N reference ranks would share the same "
+                "cores, so the per-rank-batch rate does not grow with N; a ratio against it at N GPUs compares N GPUs with one host",
     }
     emit(line)
 
@@ -314,57 +317,53 @@ def emit(line):
     out.flush()
 
 
-def main():
-    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there at the first
-    # collective) are sent to stderr for the whole run; emit() writes to the saved descriptor.
-    global _REAL_STDOUT
-    try:
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        _REAL_STDOUT = saved
-    except OSError:                                  # no usable stderr: keep the plain stdout
-        _REAL_STDOUT = None
-    args = parse_args()
-    cfg = resolve_config(args)
-    if cfg.get("stream"):
-        run_stream(args, cfg)
-        return
-    if args.impl == "reference":
-        run_reference_arm(args, cfg)
-        return
+def algorithmic_rnn_bytes(cfg):
+    G = 4 if cfg["cell"] == "lstm" else 3
+    return 12.0 * cfg["batch"] * cfg["seq_len"] * (G + 1) * cfg["hidden"]          # fwd + bwd
+
+
+def build_optimizer(cfg, rank):
+    from dotaclient_b200.optimizer import DotaOptimizer
+    return DotaOptimizer(rmq_host="bench", rmq_port=rank, epochs=1, min_seq_per_epoch=cfg["batch"], seq_len=cfg["seq_len"],
+                         learning_rate=5e-5, checkpoint=False, pretrained_model=None, mq_prefetch_count=1, log_dir=tempfile.mkdtemp(),
+                         entropy_coef=5e-4, vf_coef=0.5, run_local=True, hidden_size=cfg["hidden"], cell=cfg["cell"])
+
+
+def measure_prep(opt, rollouts, repeats=2):
+    """Experience prep of one iteration through the product's batched path (optimizer.py:328-430 for all rollouts at once):
+    host numpy rollouts -> H2D -> encoder -> recurrence -> heads -> selected log-probs -> segmented GAE -> stacked batch.
+    Returns (batch, wall ms of the last repeat, per-kernel CUDA-event ms of the last repeat)."""
+    import torch
+    from dotaclient_b200 import ops
+    batch, ms, kern = None, 0.0, {}
+    for _ in range(repeats):
+        del batch
+        torch.cuda.synchronize()
+        ops.PROFILE.reset(enabled=True)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            batch = opt.batch_from_rollouts(rollouts)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0)
+        kern = ops.PROFILE.summary(1)
+        ops.PROFILE.reset(enabled=False)
+    return batch, ms, kern
+
+
+def measure_config(cfg, args, world, rank, dev, steps, warmup, with_e2e):
+    """One BASELINE configuration on this rank's GPU: prep, `steps` timed train() calls (inputs resident in HBM), optional
+    end-to-end loops from pinned host memory.  Returns a dict of raw measurements (rank-local except the max-over-ranks ms)."""
     import torch
     import torch.distributed as dist
     from dotaclient_b200 import ops
-    from dotaclient_b200.optimizer import DotaOptimizer, ExperienceBatch
     from dotaclient_b200.synthetic import make_rollout, rollout_seed
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group(backend="nccl")
-    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
-    dev = torch.device("cuda", local_rank)
-    B, S, H, cell = cfg["batch"], cfg["seq_len"], cfg["hidden"], cfg["cell"]
-
-    opt = DotaOptimizer(rmq_host="bench", rmq_port=rank, epochs=1, min_seq_per_epoch=B, seq_len=S, learning_rate=5e-5,
-                        checkpoint=False, pretrained_model=None, mq_prefetch_count=1, log_dir=tempfile.mkdtemp(),
-                        entropy_coef=5e-4, vf_coef=0.5, run_local=True, hidden_size=H, cell=cell)
-    # synthetic experience: B rollouts of exactly S steps per rank, prepared by the product's own
-    # experiences_from_rollout (old log-probs, values, GAE under the current weights), then stacked once.
-    log("optimizer built; preparing %d rollouts of %d steps" % (B, S))
-    seqs = []
-    with torch.no_grad():
-        for i in range(B):
-            seqs.extend(opt.experiences_from_rollout(make_rollout(S, rollout_seed(rank, i))))
-    batch_dev = ExperienceBatch.from_sequences(seqs, dev)
-    del seqs
-    batch_host = batch_dev.pin_memory()
-    h2d_bytes = batch_host.nbytes()
-    torch.cuda.synchronize()
-    log("experience batch ready: %.1f MB" % (h2d_bytes / 1e6))
+    B, S = cfg["batch"], cfg["seq_len"]
+    opt = build_optimizer(cfg, rank)
+    log("[%s] optimizer built; generating %d rollouts of %d steps" % (cfg["name"], B, S))
+    rollouts = [make_rollout(S, rollout_seed(rank, i)) for i in range(B)]
+    batch_dev, prep_ms, prep_kern = measure_prep(opt, rollouts)
+    del rollouts
+    log("[%s] prep %.1f ms (batched, incl. H2D of the raw rollouts)" % (cfg["name"], prep_ms))
 
     def barrier():
         torch.cuda.synchronize()
@@ -372,11 +371,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         e1.record()
         torch.cuda.synchronize()
@@ -392,71 +391,224 @@ def main():
         opt.train(batch_dev)
         enqueue.append(opt.host_enqueue_s)
 
-    step_e2e_serial = lambda: opt.train(batch_host)  # noqa: E731   (upload, then compute)
-    pending = []
-
-    def step_e2e():
-        # double-buffered upload through the public API: step k+1's inputs start their H2D copy (from pinned host memory)
-        # before step k is launched, so the transfer runs next to step k's kernels; every timed step performs one full upload
-        cur = pending.pop() if pending else opt.prefetch(batch_host)
-        pending.append(opt.prefetch(batch_host))
-        opt.train(cur)
-
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         step_dev()
-    log("warm-up done")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ops.PROFILE.reset(enabled=True)
     if args.cuda_profiler:
         torch.cuda.profiler.start()
-    ms_total = timed(step_dev, args.steps)
+    ms_total = timed(step_dev, steps)
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
-    log("timed region (HBM-resident) done: %.2f ms/step" % (ms_total / args.steps))
-    prof = ops.PROFILE.summary(args.steps)
-    prof_bytes = dict(ops.PROFILE.bytes)
+    prof = ops.PROFILE.summary(steps)
+    prof_bytes = {k: v / steps for k, v in ops.PROFILE.bytes.items()}
     launches = ops.PROFILE.launches
     ops.PROFILE.reset(enabled=False)
-    if args.skip_e2e:
-        ms_e2e = ms_e2e_serial = float("nan")
-    else:
+    out = {"ms_per_step": ms_total / steps, "prep_ms": prep_ms, "prep_kernels": prep_kern, "kernels": prof, "kernel_bytes": prof_bytes,
+           "launches": launches, "host_enqueue_ms": 1e3 * sum(enqueue[-steps:]) / steps, "h2d_bytes": batch_dev.nbytes()}
+    log("[%s] timed region (HBM-resident): %.2f ms/step" % (cfg["name"], out["ms_per_step"]))
+    if with_e2e:
+        batch_host = batch_dev.pin_memory()
+        seqs_host = None
+        step_serial = lambda: opt.train(batch_host)  # noqa: E731   (upload, then compute)
+        pending = []
+
+        def step_e2e():
+            # double-buffered upload through the public API: step k+1's inputs start their H2D copy (from pinned host memory)
+            # before step k is launched, so the transfer runs next to step k's kernels; every timed step performs one full upload
+            cur = pending.pop() if pending else opt.prefetch(batch_host)
+            pending.append(opt.prefetch(batch_host))
+            opt.train(cur)
+
         for _ in range(2):
-            step_e2e_serial()
-        ms_e2e_serial = timed(step_e2e_serial, args.steps)
+            step_serial()
+        out["ms_e2e_serial"] = timed(step_serial, steps) / steps
         for _ in range(2):
             step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
+        out["ms_e2e"] = timed(step_e2e, steps) / steps
         pending.clear()
-    log("timed region (e2e) done: %.2f ms/step" % (ms_e2e / args.steps))
+        # the reference's own call signature: train(list_of_Sequence) with device-resident records, as its
+        # experiences_from_rollout leaves them (:355-363) -- the list is re-stacked on every call like :587-615
+        if B <= 512:
+            seqs_host = sequences_of(batch_dev)
+            for _ in range(2):
+                opt.train(seqs_host)
+            out["ms_e2e_list_api"] = timed(lambda: opt.train(seqs_host), steps) / steps
+        log("[%s] timed region (e2e): %.2f ms/step" % (cfg["name"], out["ms_e2e"]))
+        del batch_host, seqs_host
+    del batch_dev, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def sequences_of(batch):
+    """The stacked batch as the reference's ``list`` of per-sequence records (views of the device batch)."""
+    from dotaclient_b200.optimizer import Sequence
+    out = []
+    for b in range(batch.batch_size):
+        hid = (batch.h0[:, b:b + 1], batch.c0[:, b:b + 1]) if batch.c0 is not None else batch.h0[:, b:b + 1]
+        s = Sequence(game_id=0, weight_version=1, team_id=2, observations={k: v[:, b] for k, v in batch.observations.items()},
+                     actions={k: v[:, b] for k, v in batch.actions.items()}, masks={k: v[:, b] for k, v in batch.masks.items()},
+                     values=None, rewards=None, hidden=hid, old_logp=batch.old_logp[:, b])
+        s.advantages, s.returns = batch.advantages[:, b], batch.returns[:, b]
+        out.append(s)
+    return out
+
+
+def kernel_table(meas, peak):
+    table = {}
+    for name, ms in meas["kernels"].items():
+        nbytes = meas["kernel_bytes"].get(name, 0)
+        gbps = (nbytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0
+        table[name] = {"ms": ms, "bytes": nbytes, "GBps": gbps, "frac": gbps / peak}
+    return table
+
+
+def recurrence_roofline(cfg, meas, peak):
+    """The kernel north_star names: recurrence forward + backward (+ the GAE scan of the prep pass), ALGORITHMIC bytes
+    (12*N*(G+1)*H, + 16*N for GAE) over the CUDA-event time of those launches."""
+    k = meas["kernels"]
+    rnn_ms = k.get("rnn_fwd", 0.0) + k.get("rnn_bwd", 0.0)
+    by = algorithmic_rnn_bytes(cfg)
+    n_tok = cfg["batch"] * cfg["seq_len"]
+    gae_ms = meas["prep_kernels"].get("gae_scan", 0.0)
+    out = {"ms_per_step": rnn_ms, "fwd_ms": k.get("rnn_fwd", 0.0), "bwd_ms": k.get("rnn_bwd", 0.0), "algorithmic_bytes": by,
+           "GBps": by / (rnn_ms * 1e-3) / 1e9 if rnn_ms > 0 else 0.0,
+           "us_per_sequential_step": 1e3 * rnn_ms / (2 * cfg["seq_len"]) if rnn_ms > 0 else 0.0}
+    out["frac"] = out["GBps"] / peak
+    out["gae"] = {"ms": gae_ms, "algorithmic_bytes": 16.0 * n_tok, "GBps": 16.0 * n_tok / (gae_ms * 1e-3) / 1e9 if gae_ms > 0 else 0.0,
+                  "note": "prep pass (once per iteration, optimizer.py:417-421); 16 B/token is launch-latency bound at this size"}
+    tot = rnn_ms + gae_ms
+    out["lstm_plus_gae"] = {"ms": tot, "GBps": (by + 16.0 * n_tok) / (tot * 1e-3) / 1e9 if tot > 0 else 0.0}
+    out["lstm_plus_gae"]["frac"] = out["lstm_plus_gae"]["GBps"] / peak
+    return out
+
+
+def torch_cuda_baseline(cfg, steps=3, warmup=2):
+    """BASELINE.md section 3's "more honest" comparison: the reference's own train() (oracle port, stock torch ops) moved to
+    cuda:0 -- cuDNN RNN + cuBLAS + eager autograd, TF32 off so the arithmetic is fp32 like ours.  Reported next to our number;
+    like cpu_baseline it only times the oracle, nothing of it is on the product path."""
+    import copy
+    import torch
+    from oracle import ref_optimizer as RO
+    from oracle.ref_policy import RefPolicy
+    from dotaclient_b200.synthetic import make_rollout
+    dev = torch.device("cuda", torch.cuda.current_device())
+    S, H, cell, B = cfg["seq_len"], cfg["hidden"], cfg["cell"], cfg["batch"]
+    prev = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(7)
+        cpu = RO.RefOptimizer(RefPolicy(H, cell), seq_len=S)
+        proto = cpu.experiences_from_rollout(make_rollout(S, 7))[0]          # one prepared sequence, replicated B times
+
+        def to_dev(v):
+            return v.to(dev) if torch.is_tensor(v) else v
+        seqs = []
+        for _ in range(B):
+            e = copy.copy(proto)
+            e.observations = {k: to_dev(v) for k, v in proto.observations.items()}
+            e.actions = {k: to_dev(v) for k, v in proto.actions.items()}
+            e.masks = {k: to_dev(v) for k, v in proto.masks.items()}
+            e.log_probs_sel = {k: to_dev(v) for k, v in proto.log_probs_sel.items()}
+            e.hidden = tuple(to_dev(h) for h in proto.hidden) if isinstance(proto.hidden, tuple) else to_dev(proto.hidden)
+            e.advantages, e.returns = to_dev(proto.advantages), to_dev(proto.returns)
+            seqs.append(e)
+        gpu = RO.RefOptimizer(RefPolicy(H, cell).to(dev), seq_len=S)
+        for _ in range(warmup):
+            gpu.train(seqs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            gpu.train(seqs)
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / steps
+        return {"value": 1000.0 / ms, "unit": "steps/s", "ms_per_step": ms, "kind": "oracle port of optimizer.py:581-689 on cuda:0",
+                "stack": "stock torch %s eager: cuDNN GRU/LSTM, cuBLAS fp32 (TF32 off), autograd" % torch.__version__,
+                "batch": B, "steps": steps}
+    except Exception as e:                                                   # e.g. out of memory at a large config
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        torch.cuda.empty_cache()
+
+
+def main():
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version banner there at the first
+    # collective) are sent to stderr for the whole run; emit() writes to the saved descriptor.
+    global _REAL_STDOUT
+    try:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        _REAL_STDOUT = saved
+    except OSError:                                  # no usable stderr: keep the plain stdout
+        _REAL_STDOUT = None
+    args = parse_args()
+    cfg = resolve_config(args)
+    cfg["name"] = args.config
+    if cfg.get("stream"):
+        run_stream(args, cfg)
+        return
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl")
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    dev = torch.device("cuda", local_rank)
+    B, S, H, cell = cfg["batch"], cfg["seq_len"], cfg["hidden"], cfg["cell"]
+    peak, peak_src = measured_peak_hbm()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    meas = measure_config(cfg, args, world, rank, dev, args.steps, args.warmup, with_e2e=not args.skip_e2e)
     clocks = sampler.stop() if rank == 0 else None
+
+    # the other single-GPU-sized BASELINE configurations (per-GPU shapes of C1 / C3 / C4), 3 timed steps each: driver-timed
+    # evidence for every width the kernels serve.  N = 1 runs only (the scaling run times the headline workload).
+    extras = {}
+    if world == 1 and args.config == "c2" and not args.no_extra and args.batch is None and args.hidden is None and args.seq_len is None:
+        for name in ("c1", "c3", "c4"):
+            ecfg = dict(CONFIGS[name], name=name)
+            try:
+                m = measure_config(ecfg, args, world, rank, dev, 3, 3, with_e2e=False)
+                rr = recurrence_roofline(ecfg, m, peak)
+                extras[name] = {"config": workload_config(ecfg, 1, "hbm"), "ms_per_step": m["ms_per_step"],
+                                "global_optimizer_steps_per_sec": 1000.0 / m["ms_per_step"],
+                                "env_steps_per_sec": 1000.0 / m["ms_per_step"] * ecfg["batch"] * ecfg["seq_len"],
+                                "prep_ms": m["prep_ms"], "gpu_launches_per_step": m["launches"] / 3.0,
+                                "host_enqueue_ms_per_step": m["host_enqueue_ms"], "steps": 3, "warmup": 3,
+                                "roofline_recurrence": rr,
+                                "top_kernels_ms": dict(sorted(m["kernels"].items(), key=lambda kv: -kv[1])[:6])}
+            except Exception as e:                                   # never lose the headline line to an extra
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    ms_per_step = ms_total / args.steps
+    ms_per_step = meas["ms_per_step"]
     value = world * 1000.0 / ms_per_step
-    e2e_value = world * 1000.0 / (ms_e2e / args.steps)
     tokens = B * S
-    G = 4 if cell == "lstm" else 3
-    peak, peak_src = measured_peak_hbm()
     # Per-kernel table (CUDA events on the launching stream, averaged per step) with each kernel's ALGORITHMIC HBM bytes
-    # (inputs read once + outputs written once) -> achieved GB/s and fraction of the measured HBM peak.
-    table = {}
-    for name, ms in prof.items():
-        nbytes = prof_bytes.get(name, 0) / args.steps
-        table[name] = {"ms": ms, "bytes": nbytes, "GBps": (nbytes / (ms * 1e-3) / 1e9) if ms > 0 else 0.0}
-        table[name]["frac"] = table[name]["GBps"] / peak
+    # (DESIGN.md section 4: inputs read once + outputs written once) -> achieved GB/s and fraction of the measured HBM peak.
+    table = kernel_table(meas, peak)
     families = {"tcgen05 3xTF32 GEMM, forward + data gradient (dc_gemm_tf32x3*)": ["gemm_tf32x3"],
                 "tcgen05 3xTF32 weight-gradient GEMM (dc_gemm_wgrad_tf32x3*)": ["gemm_wgrad"],
                 "recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)": ["rnn_fwd", "rnn_bwd"]}
     fam = {}
     for label, names in families.items():
-        ms = sum(table[n]["ms"] for n in names if n in table)
-        by = sum(table[n]["bytes"] for n in names if n in table)
-        fam[label] = (ms, by)
+        fam[label] = (sum(table[n]["ms"] for n in names if n in table), sum(table[n]["bytes"] for n in names if n in table))
     dominant = max(fam, key=lambda k: fam[k][0])                        # the family with the largest share of the step
     dom_ms, dom_bytes = fam[dominant]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -468,29 +620,44 @@ def main():
             traffic = rec.get(families[dominant][0] if len(families[dominant]) == 1 else "rnn")
     except Exception:
         pass
-    rnn_ms, rnn_bytes = fam["recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)"]
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms,
                 "share_of_step": dom_ms / ms_per_step, "peak_source": peak_src,
-                "recurrence": {"ms_per_step": rnn_ms, "GBps": rnn_bytes / (rnn_ms * 1e-3) / 1e9 if rnn_ms > 0 else 0.0,
-                               "note": "latency-bound: 2*S=%d strictly sequential steps per optimizer step" % (2 * S)},
-                "kernels": table}
+                "recurrence": recurrence_roofline(cfg, meas, peak), "kernels": table}
     line = {
         "metric": "optimizer_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, world, "hbm"),
+        "value_definition": "n_gpus x (1000 / ms_per_step): per-GPU-batch train() steps per second summed over ranks (weak scaling). "
+                            "One data-parallel step is ONE optimizer update on an n_gpus-times larger batch: see "
+                            "global_optimizer_steps_per_sec",
+        "global_optimizer_steps_per_sec": 1000.0 / ms_per_step, "sequences_per_sec": value * B,
         "env_steps_per_sec": value * tokens,
-        "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 80,
-                "ms_per_step": ms_e2e / args.steps,
-                "mode": "double-buffered: DotaOptimizer.prefetch() uploads step k+1 from pinned host memory while step k runs",
-                "serial_value": world * 1000.0 / (ms_e2e_serial / args.steps), "serial_ms_per_step": ms_e2e_serial / args.steps},
-        "gpu_launches": launches, "host_enqueue_ms_per_step": 1e3 * sum(enqueue[-args.steps:]) / args.steps,
+        "prep": {"ms_per_iteration": meas["prep_ms"], "kernels_ms": meas["prep_kernels"],
+                 "what": "experience prep of one iteration's %d rollouts in one batched pass (optimizer.py:328-430): raw rollouts H2D, "
+                         "encoder, recurrence, heads, old log-probs, segmented GAE; runs once per iteration, train() `epochs` times" % B,
+                 "ms_per_step_prep_plus_train": meas["prep_ms"] + ms_per_step},
+        "gpu_launches": meas["launches"], "host_enqueue_ms_per_step": meas["host_enqueue_ms"],
         "roofline": roofline, "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1:      # reported baseline: rank 0 at N=1 only
+    if "ms_e2e" in meas:
+        line["e2e"] = {"value": world * 1000.0 / meas["ms_e2e"], "unit": "steps/s", "h2d_bytes_per_step": meas["h2d_bytes"],
+                       "d2h_bytes_per_step": 80, "ms_per_step": meas["ms_e2e"],
+                       "mode": "double-buffered: DotaOptimizer.prefetch() uploads step k+1 from pinned host memory while step k runs",
+                       "serial_value": world * 1000.0 / meas["ms_e2e_serial"], "serial_ms_per_step": meas["ms_e2e_serial"]}
+        if "ms_e2e_list_api" in meas:
+            line["e2e"]["reference_api_value"] = world * 1000.0 / meas["ms_e2e_list_api"]
+            line["e2e"]["reference_api_note"] = "train(list of %d device-resident Sequence records): the reference's call signature " \
+                                                "(optimizer.py:581), the list is re-stacked on every call like optimizer.py:587-615" % B
+    if extras:
+        line["extra_configs"] = extras
+    if not args.no_cpu_baseline and world == 1:      # reported baselines: rank 0 at N=1 only
+        log("timing the stock-torch cuda:0 baseline (oracle port)")
+        line["torch_cuda_baseline"] = torch_cuda_baseline(cfg)
         log("timing the CPU baseline (oracle port)")
-        v, cores, sample = cpu_reference_steps_per_sec(cfg, budget_s=20.0)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+        v, cores, sample, b_sample = cpu_reference_steps_per_sec(cfg, budget_s=20.0)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample,
+                                "sample_batch": b_sample, "scale_factor": b_sample / float(B)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

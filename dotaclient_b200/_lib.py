@@ -19,7 +19,7 @@ SIGNATURES = {
     "dc_last_error": (_c.c_char_p, []),
     "dc_device_info": (_i32, [_c.POINTER(_i32)] * 3),
     "dc_gae_scan": (_i32, [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _f64, _f64, _vp, _vp, _vp]),
-    "dc_rnn_workspace_bytes": (_sz, [_i32, _i32]),
+    "dc_rnn_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "dc_rnn_seq_fwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "dc_rnn_seq_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "dc_gemm_tf32x3_supported": (_i32, [_i64, _i32, _i32]),

@@ -5,22 +5,17 @@
 #include "dc_common.cuh"
 #include "rnn_generic.cuh"
 #include "rnn_resident.cuh"
-#include "rnn_resident2.cuh"
-#include <cstdlib>
+#include "rnn_cluster.cuh"
 
-// Two generations of weight-resident kernels exist for H = 128.  Measured on B200 at C2 (B 256, S 512, LSTM):
-//   v1 (rnn_resident.cuh, two barriers / step, partials through shared memory)  fwd 0.80 ms, bwd 0.65 ms
-//   v2 (rnn_resident2.cuh, one barrier / step, in-warp shuffle reduction)       fwd 0.95 ms, bwd 0.84 ms
-// v1 is the default; DC_RNN_V2=1 selects v2 for A/B measurements (both are parity-tested).
-static bool use_v1() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("DC_RNN_V2"); v = (e && e[0] == '1') ? 0 : 1; }
-    return v == 1;
-}
+// Kernel selection by width (no environment switches, no library fallback):
+//   H == 128  rnn_resident.cuh  W_hh resident in registers + shared memory of ONE SM, packed-fp32 FFMA2
+//   H == 256  rnn_cluster.cuh   W_hh resident in tensor memory + shared memory of an 8-CTA cluster, tcgen05 3xTF32
+//   other H   rnn_generic.cuh   W_hh streamed from L2 every step (correct for any H % 4 == 0)
 
-extern "C" size_t dc_rnn_workspace_bytes(int cell, int H) {
+extern "C" size_t dc_rnn_workspace_bytes(int cell, int B, int H) {
     const int G = cell == DC_CELL_GRU ? 3 : 4;
-    return (size_t)G * H * H * sizeof(float);   // W_hh^T for the generic forward
+    if (dc_rnnc::cluster_supported(H)) return dc_rnnc::bwd_workspace_bytes(B > 0 ? B : 1);   // partial-sum exchange (backward)
+    return (size_t)G * H * H * sizeof(float);   // W_hh^T for the forward kernels that read the transpose
 }
 
 static int check_rnn_args(const char *fn, int cell, int B, int S, int H) {
@@ -37,8 +32,7 @@ extern "C" int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const f
     DC_REQUIRE(gates && w_hh && b_hh && ybuf && cbuf && workspace, DC_EINVAL, "dc_rnn_seq_fwd: null pointer");
     cudaStream_t st = dc_cu_stream(stream);
     const int G = cell == DC_CELL_GRU ? 3 : 4;
-    if (dc_rnn::resident_supported(cell, H) && !use_v1())
-        return dc_rnn2::launch_fwd(cell, gates, w_hh, b_hh, ybuf, cbuf, B, S, st);   // reads W_hh as stored
+    if (dc_rnnc::cluster_supported(H)) return dc_rnnc::launch_fwd(cell, gates, w_hh, b_hh, ybuf, cbuf, B, S, st);   // reads W_hh as stored
     // the other forward kernels read W_hh^T [H, G*H] so that output columns are contiguous (coalesced / float4)
     float *wT = reinterpret_cast<float *>(workspace);
     dim3 tb(32, 8), tg((H + 31) / 32, (G * H + 31) / 32);
@@ -61,14 +55,15 @@ extern "C" int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const f
 extern "C" int dc_rnn_seq_bwd(int cell, float *gates, const float *w_hh, const float *ybuf, float *cbuf, const float *dy,
                               const float *dhn, const float *dcn, float *dh0, float *dc0, int B, int S, int H,
                               void *workspace, dc_stream_t stream) {
-    (void)workspace;
     int rc = check_rnn_args("dc_rnn_seq_bwd", cell, B, S, H);
     if (rc) return rc;
     DC_REQUIRE(gates && w_hh && ybuf && cbuf && dy, DC_EINVAL, "dc_rnn_seq_bwd: null pointer");
     cudaStream_t st = dc_cu_stream(stream);
     const int G = cell == DC_CELL_GRU ? 3 : 4;
-    if (dc_rnn::resident_supported(cell, H) && !use_v1())
-        return dc_rnn2::launch_bwd(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, st);
+    if (dc_rnnc::cluster_supported(H)) {
+        DC_REQUIRE(workspace, DC_EINVAL, "dc_rnn_seq_bwd: the H = 256 kernels need the workspace (dc_rnn_workspace_bytes)");
+        return dc_rnnc::launch_bwd(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, reinterpret_cast<float *>(workspace), B, S, st);
+    }
     if (dc_rnn::resident_supported(cell, H))
         return dc_rnn::launch_bwd_resident(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, H, st);
     const int blocks = (B + dc_rnn::kBT - 1) / dc_rnn::kBT;

@@ -141,12 +141,12 @@ def gae_scan(rewards, values, seg_off, gamma=0.98, lam=0.97, boot_value=None, bo
 _workspaces = {}
 
 
-def _rnn_workspace(cell, H, device):
+def _rnn_workspace(cell, B, H, device):
     key = (cell, H, device)
+    nbytes = max(int(_lib.load().dc_rnn_workspace_bytes(CELL_ID[cell], B, H)), 16)
     ws = _workspaces.get(key)
-    if ws is None:
-        nbytes = _lib.load().dc_rnn_workspace_bytes(CELL_ID[cell], H)
-        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
 
@@ -178,7 +178,7 @@ def _rnn_forward_impl(x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
     ybuf[0].copy_(h0.detach().reshape(B, H))
     if cell == "lstm":
         cbuf[0].copy_(c0.detach().reshape(B, H))
-    ws = _rnn_workspace(cell, H, x.device)
+    ws = _rnn_workspace(cell, B, H, x.device)
     lib = _lib.load()
     with PROFILE.span("rnn_fwd", 1, 4 * S * B * ((4 if cell == "lstm" else 3) + 1) * H):
         _lib.check(lib.dc_rnn_seq_fwd(CELL_ID[cell], gates.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(),
@@ -233,7 +233,7 @@ class RnnSequence(torch.autograd.Function):
         dcn = _f32c(dcn) if (dcn is not None and cell == "lstm" and dcn.numel()) else None
         dh0 = torch.empty((B, H), dtype=torch.float32, device=x2.device)
         dc0 = torch.empty((B, H), dtype=torch.float32, device=x2.device) if cell == "lstm" else None
-        ws = _rnn_workspace(cell, H, x2.device)
+        ws = _rnn_workspace(cell, B, H, x2.device)
         lib = _lib.load()
         with PROFILE.span("rnn_bwd", 1, 8 * S * B * ((4 if cell == "lstm" else 3) + 1) * H):
             _lib.check(lib.dc_rnn_seq_bwd(CELL_ID[cell], gates.data_ptr(), w_hh.data_ptr(), ybuf.data_ptr(),

@@ -496,23 +496,26 @@ class DotaOptimizer:
             sequences.append(seq)
         return sequences
 
-    def experiences_from_rollouts(self, datas):
-        """All rollouts of an iteration in ONE batched no-grad pass: the rollouts become the batch
-        dimension of a single time-major ``[L_max, R, ...]`` forward (encoder chain, recurrence from the zero state, heads,
-        selected log-probs) and one segmented GAE scan over all of them, instead of ``R`` batch-1 passes whose recurrence
-        runs on a single SM.  Per rollout the result equals ``experiences_from_rollout`` (:328-430): own padding to a
-        multiple of ``seq_len``, own terminal bootstrap, chunks beyond its padded length are not emitted."""
+    def _prepare_rollouts(self, datas):
+        """The batched no-grad half of an iteration: all rollouts become the batch dimension of ONE
+        time-major ``[L_max, R, ...]`` pass -- encoder chain, recurrence from the zero state, heads, selected log-probs
+        (:384-390) -- followed by ONE segmented GAE scan over every rollout's own padded length (:417-421).  Returns the raw
+        device tensors; ``experiences_from_rollouts`` / ``batch_from_rollouts`` slice them."""
         S, dev, pol = self.seq_len, self.device, self.policy_base
         R = len(datas)
         Ls = [int(d['rewards'].shape[0]) for d in datas]
         Lps = [(L + S - 1) // S * S for L in Ls]
         Lmax = max(Lps)
+        same = all(L == Lmax for L in Ls)
 
         def batched(group, key, dtype):
-            first = np.asarray(datas[0][group][key])
-            host = np.zeros((Lmax, R) + tuple(first.shape[1:]), dtype=dtype)           # zero padding (:367-382)
-            for i, d in enumerate(datas):
-                host[:Ls[i], i] = np.asarray(d[group][key])
+            if same:                                                                   # no padding anywhere: one stack
+                host = np.stack([np.asarray(d[group][key]) for d in datas], axis=1).astype(dtype, copy=False)
+            else:
+                first = np.asarray(datas[0][group][key])
+                host = np.zeros((Lmax, R) + tuple(first.shape[1:]), dtype=dtype)       # zero padding (:367-382)
+                for i, d in enumerate(datas):
+                    host[:Ls[i], i] = np.asarray(d[group][key])
             return torch.from_numpy(host).to(dev, non_blocking=True)
 
         obs = {k: batched('observations', k, np.float32) for k in Policy.INPUT_KEYS}
@@ -532,12 +535,26 @@ class DotaOptimizer:
             keys = ops.HEAD_KEYS
             old_logp = ops.selected_logp([logits[k] for k in keys], [masks[k] for k in keys],
                                          [actions[k] for k in keys]).view(Lmax, R, 5)        # :387-390
-            # GAE per rollout over ITS padded length: compact the [L_max, R] value grid into back-to-back segments
+            # GAE per rollout over ITS padded length: back-to-back segments, rollout-major
             values_lr = values.reshape(Lmax, R)
-            vals_c = torch.cat([values_lr[:Lps[i], i] for i in range(R)])
-            rew_c = torch.from_numpy(np.concatenate([rewards_np[i, :Lps[i]] for i in range(R)])).to(dev)
+            if same:
+                vals_c = values_lr.t().reshape(-1)
+                rew_c = torch.from_numpy(rewards_np.reshape(R * Lmax, -1)).to(dev, non_blocking=True)
+            else:
+                vals_c = torch.cat([values_lr[:Lps[i], i] for i in range(R)])
+                rew_c = torch.from_numpy(np.concatenate([rewards_np[i, :Lps[i]] for i in range(R)])).to(dev)
             seg = torch.tensor(np.concatenate([[0], np.cumsum(Lps)]), dtype=torch.int64, device=dev)
             adv_c, ret_c = ops.gae_scan(rew_c, vals_c, seg, gamma=GAMMA, lam=LAMBDA)          # :417-421
+        return dict(obs=obs, masks=masks, actions=actions, rewards_np=rewards_np, old_logp=old_logp, values_lr=values_lr,
+                    adv_c=adv_c, ret_c=ret_c, ybuf=ybuf, cbuf=cbuf, Ls=Ls, Lps=Lps, Lmax=Lmax, same=same)
+
+    def experiences_from_rollouts(self, datas):
+        """``experiences_from_rollout`` (:328-430) for all rollouts of an iteration at once: per rollout the result equals the
+        per-rollout path -- own padding to a multiple of ``seq_len``, own terminal bootstrap, chunks beyond its padded
+        length are not emitted -- but the work is one batched pass instead of ``R`` batch-1 passes."""
+        S, pol = self.seq_len, self.policy_base
+        p = self._prepare_rollouts(datas)
+        obs, masks, actions, ybuf, cbuf, Lps = p['obs'], p['masks'], p['actions'], p['ybuf'], p['cbuf'], p['Lps']
         out = []
         for i, d in enumerate(datas):
             base = int(sum(Lps[:i]))
@@ -552,13 +569,28 @@ class DotaOptimizer:
                                observations={k: v[sl, i] for k, v in obs.items()},
                                actions={k: v[sl, i] for k, v in actions.items()},
                                masks={k: v[sl, i] for k, v in masks.items()},
-                               values=values_lr[sl, i].reshape(1, S, 1), rewards=rewards_np[i, sl], hidden=hid,
-                               old_logp=old_logp[sl, i])
-                seq.advantages = adv_c[base + j * S: base + (j + 1) * S]
-                seq.returns = ret_c[base + j * S: base + (j + 1) * S]
+                               values=p['values_lr'][sl, i].reshape(1, S, 1), rewards=p['rewards_np'][i, sl], hidden=hid,
+                               old_logp=p['old_logp'][sl, i])
+                seq.advantages = p['adv_c'][base + j * S: base + (j + 1) * S]
+                seq.returns = p['ret_c'][base + j * S: base + (j + 1) * S]
                 sequences.append(seq)
             out.append(sequences)
         return out
+
+    def batch_from_rollouts(self, datas):
+        """Rollouts -> one stacked, time-major ``ExperienceBatch`` (what ``train`` consumes; :587-615 stacks the same
+        sequences batch-first).  When every rollout is exactly one ``seq_len`` chunk the prepared tensors ARE the batch (no
+        per-sequence slicing or re-stacking); otherwise the chunks go through ``ExperienceBatch.from_sequences``."""
+        S = self.seq_len
+        if all(int(d['rewards'].shape[0]) == S for d in datas):
+            p = self._prepare_rollouts(datas)
+            R = len(datas)
+            h0 = torch.zeros((1, R, self.policy_base.hidden_size), dtype=torch.float32, device=self.device)
+            c0 = torch.zeros_like(h0) if self.policy_base.cell == "lstm" else None
+            return ExperienceBatch(p['obs'], p['masks'], p['actions'], p['old_logp'], p['adv_c'].view(R, S).t().contiguous(),
+                                   p['ret_c'].view(R, S).t().contiguous(), h0, c0)
+        seqs = [s for group in self.experiences_from_rollouts(datas) for s in group]
+        return ExperienceBatch.from_sequences(seqs, self.device)
 
     @staticmethod
     def list_of_dicts_to_dict_of_lists(x):
@@ -667,9 +699,9 @@ class DotaOptimizer:
             weight_ages.append(it - weight_version)
         for sequences in self.experiences_from_rollouts(rollouts):
             experiences.extend(sequences)
+        batch = ExperienceBatch.from_sequences(experiences, self.device)  # stacked once, reused by every epoch
         time_xp = time.time() - start_xp
 
-        batch = ExperienceBatch.from_sequences(experiences, self.device)  # stacked once, reused by every epoch
         losses, entropies, grad_norms = [], [], []
         start_optimizing = time.time()
         for ep in range(self.epochs):                                      # :469

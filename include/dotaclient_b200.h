@@ -71,14 +71,17 @@ int dc_gae_scan(const float *rewards, int n_sub, const float *values, const int6
  *   ybuf   [S+1, B, H]  slot 0 = h_0 (in), slot t+1 = h_t (out)   -> y = ybuf[1:], h_n = ybuf[S]
  *   cbuf   [S+1, B, H]  LSTM: slot 0 = c_0 (in), slot t+1 = c_t (out)
  *                       GRU : slot t+1 = W_hn h_{t-1} + b_hn (out, saved for backward)
- *   workspace: dc_rnn_workspace_bytes(cell, H) bytes of scratch.
+ *   workspace: dc_rnn_workspace_bytes(cell, B, H) bytes of scratch (W_hh^T for H != 256; at H = 256 the partial-sum
+ *              exchange of the cluster backward kernel -- the same buffer serves forward and backward).
+ * Kernels by width: H = 128 one-SM weight-resident FFMA2 kernels; H = 256 (the reference's width) 8-CTA-cluster
+ * tensor-memory-resident tcgen05 3xTF32 kernels; any other H % 4 == 0 a generic kernel that streams W_hh from L2.
  * Backward (consumes what forward left behind)
  *   gates  in: activated gates   out: dL/d(gates pre-activation wrt the i2h branch) = dgi
  *   cbuf   LSTM: unchanged.  GRU: slot t+1 out = dL/d(W_hn h + b_hn) (the n-gate part of dgh)
  *   dy     [S, B, H]  dL/dy (time-major); dhn/dcn [B, H] or NULL (gradient of the final state)
  *   dh0/dc0 [B, H] or NULL outputs.
  */
-size_t dc_rnn_workspace_bytes(int cell, int H);
+size_t dc_rnn_workspace_bytes(int cell, int B, int H);
 int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const float *b_hh, float *ybuf,
                    float *cbuf, int B, int S, int H, void *workspace, dc_stream_t stream);
 int dc_rnn_seq_bwd(int cell, float *gates, const float *w_hh, const float *ybuf, float *cbuf,

@@ -41,7 +41,8 @@ def test_version_and_argument_errors_without_gpu(lib):
     assert rc == -1 and b"unknown cell" in lib.dc_last_error()
     rc = lib.dc_rnn_seq_fwd(1, None, None, None, None, None, 1, 1, 130, None, None)
     assert rc == -2
-    assert lib.dc_rnn_workspace_bytes(1, 128) == 4 * 128 * 128 * 4
+    assert lib.dc_rnn_workspace_bytes(1, 7, 128) == 4 * 128 * 128 * 4
+    assert lib.dc_rnn_workspace_bytes(0, 33, 256) == 2 * 2 * 8 * 32 * 256 * 4      # two clusters, ping-pong partials
 
 
 def test_sass_is_sm100a_only():

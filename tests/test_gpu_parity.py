@@ -125,7 +125,7 @@ def _torch_rnn(cell, H):
 
 @pytest.mark.parametrize("cell", ["gru", "lstm"])
 @pytest.mark.parametrize("B,S,H", [(3, 7, 128), (2, 40, 128), (5, 16, 256), (2, 5, 512), (9, 33, 128), (1, 1, 64),
-                                   (301, 6, 128), (1, 3, 128)])
+                                   (301, 6, 128), (1, 3, 128), (1, 1, 256), (33, 9, 256), (64, 128, 256), (70, 130, 512)])
 def test_rnn_forward_backward_vs_torch(cell, B, S, H):
     """Recurrence kernels (+ cuBLAS i2h) against torch.nn.GRU / nn.LSTM on CPU: outputs, final state, all grads."""
     from dotaclient_b200 import ops
@@ -169,12 +169,13 @@ def test_rnn_forward_backward_vs_torch(cell, B, S, H):
         torch.testing.assert_close(p[k].grad.cpu(), v.grad, rtol=5e-4, atol=5e-6 * scale * B)
 
 
-@pytest.mark.parametrize("cell,H", [("lstm", 128), ("gru", 128)])
-def test_rnn_full_size_sampled_sequences(cell, H):
-    """C2 shape (B=256, S=512, H=128): sequences are independent, so sampled rows must match the CPU oracle run on
-    just those rows; state must carry across a split at S/2 (truncated-BPTT chunking, optimizer.py:343-385)."""
+@pytest.mark.parametrize("cell,H,B", [("lstm", 128, 256), ("gru", 128, 256), ("lstm", 256, 512), ("gru", 256, 512)])
+def test_rnn_full_size_sampled_sequences(cell, H, B):
+    """C2 shape (B=256, S=512, H=128) and C3's per-GPU shape (B=512, S=512, H=256): sequences are independent, so sampled
+    rows must match the CPU oracle run on just those rows; state must carry across a split at S/2 (truncated-BPTT
+    chunking, optimizer.py:343-385)."""
     from dotaclient_b200 import ops
-    B, S = 256, 512
+    S = 512
     torch.manual_seed(11)
     ref = _torch_rnn(cell, H)
     x = torch.randn(S, B, H) * 0.7
@@ -184,7 +185,7 @@ def test_rnn_full_size_sampled_sequences(cell, H):
     c0 = torch.zeros(B, H, device=d) if cell == "lstm" else None
     with torch.no_grad():
         y, hn, cn = ops.rnn_sequence(x.to(d), p["weight_ih_l0"], p["weight_hh_l0"], p["bias_ih_l0"], p["bias_hh_l0"], h0, c0, cell)
-        rows = [0, 1, 100, 255]
+        rows = [0, 1, 100, B - 1]
         xs = x[:, rows]
         z = torch.zeros(1, len(rows), H)
         yr = ref(xs, (z, z) if cell == "lstm" else z)[0]

@@ -56,13 +56,16 @@ def bench(cell, B, S, H):
     t_ours = timeit(ours, n)
     prof = ops.PROFILE.summary(n + 2)
     ops.PROFILE.reset(enabled=False)
-    t_ref = timeit(cudnn, n)
+    t_ref = timeit(cudnn, n)                       # cuDNN default: TF32 tensor cores allowed (torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    t_ref32 = timeit(cudnn, n)                     # cuDNN restricted to fp32 arithmetic (the like-for-like comparison)
+    torch.backends.cudnn.allow_tf32 = True
     fwd, bwd = prof.get("rnn_fwd", 0.0), prof.get("rnn_bwd", 0.0)
     nbytes = 12.0 * S * B * (G + 1) * H
     print("%-4s B=%4d S=%4d H=%3d | fwd %.3f ms (%.2f us/step) bwd %.3f ms (%.2f us/step) | %.0f GB/s algorithmic | "
-          "layer fwd+bwd incl. GEMMs: ours %.3f ms, cuDNN %.3f ms | max|y - cudnn| %.2e"
+          "layer fwd+bwd incl. GEMMs: ours %.3f ms, cuDNN(tf32) %.3f ms, cuDNN(fp32) %.3f ms | max|y - cudnn| %.2e"
           % (cell, B, S, H, fwd, 1e3 * fwd / S, bwd, 1e3 * bwd / S, nbytes / ((fwd + bwd) * 1e-3) / 1e9 if fwd + bwd > 0 else 0.0,
-             t_ours, t_ref, err))
+             t_ours, t_ref, t_ref32, err))
 
 
 def main():
@@ -70,7 +73,7 @@ def main():
         shapes = [(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))]
     else:
         shapes = [("lstm", 256, 512, 128), ("gru", 256, 512, 128), ("lstm", 128, 512, 128), ("lstm", 512, 512, 128),
-                  ("gru", 512, 512, 256), ("lstm", 512, 256, 512)]
+                  ("gru", 512, 512, 256), ("lstm", 512, 512, 256), ("gru", 1024, 16, 256), ("lstm", 512, 1024, 512)]
     for s in shapes:
         bench(*s)
 
