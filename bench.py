@@ -393,18 +393,25 @@ def measure_config(cfg, args, world, rank, dev, steps, warmup, with_e2e):
 
     for _ in range(max(3, warmup)):
         step_dev()
-    ops.PROFILE.reset(enabled=True)
+    # (1) the headline: train() on a device-resident batch -- after the warm-up the step replays from its CUDA graph
     if args.cuda_profiler:
         torch.cuda.profiler.start()
     ms_total = timed(step_dev, steps)
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
+    enq = 1e3 * sum(enqueue[-steps:]) / steps
+    graphed = any(isinstance(v, tuple) for v in opt._graphs.values())
+    # (2) the same steps launch by launch with CUDA events around every C-ABI call: the per-kernel table of the roofline
+    ops.PROFILE.reset(enabled=True)
+    ms_eager = timed(step_dev, steps)
     prof = ops.PROFILE.summary(steps)
     prof_bytes = {k: v / steps for k, v in ops.PROFILE.bytes.items()}
     launches = ops.PROFILE.launches
     ops.PROFILE.reset(enabled=False)
-    out = {"ms_per_step": ms_total / steps, "prep_ms": prep_ms, "prep_kernels": prep_kern, "kernels": prof, "kernel_bytes": prof_bytes,
-           "launches": launches, "host_enqueue_ms": 1e3 * sum(enqueue[-steps:]) / steps, "h2d_bytes": batch_dev.nbytes()}
+    out = {"ms_per_step": ms_total / steps, "ms_per_step_launch_by_launch": ms_eager / steps, "cuda_graph": graphed,
+           "prep_ms": prep_ms, "prep_kernels": prep_kern, "kernels": prof, "kernel_bytes": prof_bytes,
+           "launches": launches, "host_enqueue_ms": enq, "host_enqueue_ms_launch_by_launch": 1e3 * sum(enqueue[-steps:]) / steps,
+           "h2d_bytes": batch_dev.nbytes()}
     log("[%s] timed region (HBM-resident): %.2f ms/step" % (cfg["name"], out["ms_per_step"]))
     if with_e2e:
         batch_host = batch_dev.pin_memory()
@@ -585,7 +592,8 @@ def main():
                 extras[name] = {"config": workload_config(ecfg, 1, "hbm"), "ms_per_step": m["ms_per_step"],
                                 "global_optimizer_steps_per_sec": 1000.0 / m["ms_per_step"],
                                 "env_steps_per_sec": 1000.0 / m["ms_per_step"] * ecfg["batch"] * ecfg["seq_len"],
-                                "prep_ms": m["prep_ms"], "gpu_launches_per_step": m["launches"] / 3.0,
+                                "prep_ms": m["prep_ms"], "gpu_launches_per_step": m["launches"] / 3.0, "cuda_graph": m["cuda_graph"],
+                                "ms_per_step_launch_by_launch": m["ms_per_step_launch_by_launch"],
                                 "host_enqueue_ms_per_step": m["host_enqueue_ms"], "steps": 3, "warmup": 3,
                                 "roofline_recurrence": rr,
                                 "top_kernels_ms": dict(sorted(m["kernels"].items(), key=lambda kv: -kv[1])[:6])}
@@ -638,6 +646,11 @@ def main():
                          "encoder, recurrence, heads, old log-probs, segmented GAE; runs once per iteration, train() `epochs` times" % B,
                  "ms_per_step_prep_plus_train": meas["prep_ms"] + ms_per_step},
         "gpu_launches": meas["launches"], "host_enqueue_ms_per_step": meas["host_enqueue_ms"],
+        "launch": {"cuda_graph": meas["cuda_graph"], "kernels_per_step": meas["launches"] / float(args.steps),
+                   "ms_per_step_launch_by_launch": meas["ms_per_step_launch_by_launch"],
+                   "host_enqueue_ms_per_step_launch_by_launch": meas["host_enqueue_ms_launch_by_launch"],
+                   "note": "value/ms_per_step: the step replayed from its CUDA graph (one graph launch per step, same kernels); the "
+                           "per-kernel table of `roofline` is measured launch by launch with CUDA events around every call"},
         "roofline": roofline, "clocks": clocks,
     }
     if "ms_e2e" in meas:

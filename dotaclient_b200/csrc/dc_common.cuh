@@ -32,6 +32,10 @@ static inline cudaStream_t dc_cu_stream(dc_stream_t s) { return reinterpret_cast
 // Number of SMs of the current device (cached per device; 148 on B200).
 int dc_sm_count();
 
+// csrc/gemm_tf32x3.cu: split-K tcgen05 3xTF32 GEMM writing `ksplit` partial [M, N] products (library-internal).
+int dc_gemm_tf32x3_splitk(const float *A, int lda, const float *B, int ldb, float *part, int64_t M, int N, int K, int ksplit,
+                          bool first_call, cudaStream_t st);
+
 __device__ __forceinline__ float dc_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
 // tanh via one exp; abs error ~1e-7, saturates cleanly for |x| large.
 __device__ __forceinline__ float dc_tanh(float x) { return 1.0f - 2.0f / (__expf(2.0f * x) + 1.0f); }

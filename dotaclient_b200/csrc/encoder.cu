@@ -542,11 +542,8 @@ extern "C" int dc_unit_basic_bwd(const float *d_basic, const float *basic, const
     int blocks;
     if ((((uintptr_t)units) & 15) == 0) {                      // bulk copies need 16-byte aligned sources
         blocks = dc_sm_count();
-        static bool attr_set = false;
-        if (!attr_set) {
-            DC_CUDA(cudaFuncSetAttribute(unit_basic_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
-            attr_set = true;
-        }
+        // per-device attribute: set on every call (a process-wide "done" flag breaks the second GPU of a process)
+        DC_CUDA(cudaFuncSetAttribute(unit_basic_bwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem));
         unit_basic_bwd_tma_kernel<<<blocks, kThreadsE, kBwdSmem, st>>>(d_basic, basic, units, R, partial);
     } else {
         blocks = 2 * dc_sm_count();

@@ -9,15 +9,14 @@
 //   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, three tcgen05.mma.kind::tf32 per k-step into one fp32
 //   TMEM accumulator.  The dropped a_lo*b_lo term and the truncation of the lo parts are O(2^-22).
 //
-// Four kernels share the building blocks below (one persistent CTA per SM, warp-specialised, 17 warps):
+// Three kernels share the building blocks below (one persistent CTA per SM, warp-specialised, 17 warps):
 //   gemm_tf32x3_kernel        any K: A and B both stream through a 3-stage shared-memory ring (4 tiles of 16 KB per stage:
 //                             A_hi, A_lo, B_hi, B_lo); used for K > 128 (affine_pre_rnn, the i2h data gradient).
 //   gemm_tf32x3_wtmem_kernel  K <= 128 (nearly every layer of this model): the TRANSPOSED product with the weight block
 //                             resident in tensor memory as the A operand; activations through a 6-stage ring; an epilogue
 //                             thread owns one output feature.  See the comment above the kernel.
-//   gemm_tf32x3_bres_kernel   K <= 128 fallback (DC_GEMM_WTMEM=0): weight block resident in shared memory.
-//   gemm_wgrad_atmem_kernel   weight gradient dW = dY^T X (split-K), dY^T fed to the MMAs from tensor memory
-//                             (gemm_wgrad_kernel: both operands through shared memory, DC_WGRAD_ATMEM=0).
+//   gemm_wgrad_atmem_kernel   weight gradient dW = dY^T X (split-K), dY^T fed to the MMAs from tensor memory.
+// (The round-1 variants with the weight block / both wgrad operands in shared memory were measured slower and are gone.)
 // Roles in every kernel:
 //   PRODUCER warps (groups of 4 taking alternate k-chunks, so the global-load latency of one chunk overlaps the split
 //              arithmetic of another): coalesced global loads of a [128 x 32] fp32 chunk, hi/lo split on the CUDA cores,
@@ -31,7 +30,6 @@
 // Tensor-pipe work: 2*M*N*K*3 flops; HBM: 4*(M*K + N*K + M*N) bytes.  For the K=128 GEMMs of this model the kernels are
 // HBM-bound even with the 3x flops (measured: 5.2-5.5 TB/s on the 2M x 128 x 128 layers).
 #include "dc_common.cuh"
-#include <cstdlib>
 
 namespace {
 
@@ -171,7 +169,10 @@ __device__ __forceinline__ void store_row32(float *dst, const uint32_t (&r)[32],
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *__restrict__ A, RowMap amap,
                                                                   const float *__restrict__ B, int ldb,
                                                                   const float *__restrict__ bias, float *__restrict__ C,
-                                                                  RowMap cmap, int M, int N, int K, int relu, bool wide) {
+                                                                  RowMap cmap, int M, int N, int K, int relu, bool wide,
+                                                                  int ksplit, long long c_split_stride) {
+    // ksplit > 1: split-K -- work item = (K range sp, output tile); range sp writes its partial product to
+    // C + sp * c_split_stride (the caller sums the partials in a fixed order), bias goes with range 0.
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
@@ -179,8 +180,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
-    const int tiles_total = m_blocks * n_blocks;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK / ksplit;      // chunks per K range
+    const int tiles_mn = m_blocks * n_blocks, tiles_total = tiles_mn * ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
@@ -201,15 +202,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
         const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
         uint32_t chunk = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
-            const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+            const int tmn = tile % tiles_mn, kc0 = (tile / tiles_mn) * k_chunks;
+            const int m0 = (tmn / n_blocks) * BM, n0 = (tmn % n_blocks) * BN;
             for (int kc = 0; kc < k_chunks; ++kc, ++chunk) {
                 if ((int)(chunk % kProducerGroups) != g) continue;
                 const int stage = chunk % kStages;
                 const uint32_t phase = (chunk / kStages) & 1;
                 mbar_wait(&empty[stage], phase ^ 1);
                 unsigned char *st = tiles + (size_t)stage * kStageBytes;
-                produce_tile(A, amap, m0, M, kc * BK, st, st + kTileBytes, t);
-                produce_tile(B, RowMap{ldb, 0, 0, 0, 0}, n0, N, kc * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
+                produce_tile(A, amap, m0, M, (kc0 + kc) * BK, st, st + kTileBytes, t);
+                produce_tile(B, RowMap{ldb, 0, 0, 0, 0}, n0, N, (kc0 + kc) * BK, st + 2 * kTileBytes, st + 3 * kTileBytes, t);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
@@ -253,11 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
         int it = 0;
         for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, ++it) {
             const int a = it & 1;
-            const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+            const int tmn = tile % tiles_mn, sp = tile / tiles_mn;
+            const int m0 = (tmn / n_blocks) * BM, n0 = (tmn % n_blocks) * BN;
             mbar_wait(&acc_full[a], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + q * 32 + lane;
-            float *crow = C + cmap.off(row < M ? row : 0) + n0;
+            float *crow = C + (size_t)sp * (size_t)c_split_stride + cmap.off(row < M ? row : 0) + n0;
+            const float *tile_bias = (bias && sp == 0) ? bias : nullptr;
 #pragma unroll 1
             for (int cb = 0; cb < BN; cb += 32) {
                 uint32_t r[32];
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
+                if (row < M) store_row32(crow + cb, r, tile_bias ? tile_bias + n0 + cb : nullptr, relu, wide);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -288,148 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
 }
 
 
-// =================================================================================================
-// K <= 128 specialisation (the unit-embedding GEMMs and the i2h projection at H = 128): the whole B operand of the
-// CTA's column block (<= 128 x 128, hi + lo = 128 KB) is split ONCE and stays resident in shared memory; the ring
-// stages carry only A (hi + lo, 32 KB each).  Every CTA owns one column block and walks the row blocks, and every
-// producer group keeps the next chunk's eight loads in flight while it splits the current one.
-constexpr int kStageBytesA = 2 * kTileBytes;
-constexpr int kMaxResChunks = 4;
-constexpr size_t kSmemBytesBRes = (size_t)kMaxResChunks * 2 * kTileBytes + (size_t)kStages * kStageBytesA + 1024 + 128;
-
-__global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_bres_kernel(const float *__restrict__ A, RowMap amap,
-                                                                       const float *__restrict__ B, int ldb,
-                                                                       const float *__restrict__ bias, float *__restrict__ C,
-                                                                       RowMap cmap, int M, int N, int K, int relu, bool wide) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *bres = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *tiles = bres + (size_t)kMaxResChunks * 2 * kTileBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytesA);
-    uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages, *acc_empty = bars + 2 * kStages + 2;
-    uint64_t *b_ready = bars + 2 * kStages + 4;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 5);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
-    const int n_blk = blockIdx.x % n_blocks, m_first = blockIdx.x / n_blocks, m_step = gridDim.x / n_blocks;
-    const int n0 = n_blk * BN;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
-        mbar_init(b_ready, kProducerThreads * kProducerGroups / 32);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < kMmaWarp) {
-        // ===== PRODUCERS =====
-        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
-        for (int kc = g; kc < k_chunks; kc += kProducerGroups)            // the resident B block, once
-            produce_tile(B, RowMap{ldb, 0, 0, 0, 0}, n0, N, kc * BK, bres + (size_t)kc * 2 * kTileBytes,
-                         bres + (size_t)kc * 2 * kTileBytes + kTileBytes, t);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(b_ready);
-        // A chunks: running chunk index c = tile_iter * k_chunks + kc; this group takes c == g (mod groups)
-        const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
-        const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
-        float4 v[8], vn[8];
-        uint32_t c = g;
-        if (c < total_chunks) tile_load_k(A, amap, (m_first + (int)(c / k_chunks) * m_step) * BM, M, (int)(c % k_chunks) * BK, t, v);
-        for (; c < total_chunks; c += kProducerGroups) {
-            const uint32_t cn = c + kProducerGroups;
-            if (cn < total_chunks)
-                tile_load_k(A, amap, (m_first + (int)(cn / k_chunks) * m_step) * BM, M, (int)(cn % k_chunks) * BK, t, vn);
-            const int stage = c % kStages;
-            mbar_wait(&empty[stage], ((c / kStages) & 1) ^ 1);
-            unsigned char *st = tiles + (size_t)stage * kStageBytesA;
-            tile_store_k(v, st, st + kTileBytes, t);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);        // one arrival per warp (128 single arrivals serialise on the barrier)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = vn[i];
-        }
-    } else if (warp == kMmaWarp) {
-        // ===== MMA ISSUER =====
-        mbar_wait(b_ready, 0);
-        uint32_t c = 0;
-        int it = 0;
-        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
-            const int a = it & 1;
-            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_d = tmem_base + a * kAccCols;
-            for (int kc = 0; kc < k_chunks; ++kc, ++c) {
-                const int stage = c % kStages;
-                mbar_wait(&full[stage], (c / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane == 0) {
-                    const uint32_t abase = smem_u32(tiles + (size_t)stage * kStageBytesA);
-                    const uint32_t bbase = smem_u32(bres + (size_t)kc * 2 * kTileBytes);
-                    const uint64_t a_hi = make_desc(abase), a_lo = make_desc(abase + kTileBytes);
-                    const uint64_t b_hi = make_desc(bbase), b_lo = make_desc(bbase + kTileBytes);
-#pragma unroll
-                    for (int ks = 0; ks < BK / 8; ++ks) {
-                        const uint64_t adv = (uint64_t)(ks * 2);
-                        const uint32_t first = (kc | ks) != 0;
-                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, kIdesc, first);
-                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1u);
-                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, kIdesc, 1u);
-                    }
-                    umma_commit(&empty[stage]);
-                    if (kc == k_chunks - 1) umma_commit(&acc_full[a]);
-                }
-                __syncwarp();
-            }
-        }
-    } else {
-        // ===== EPILOGUE =====
-        const int q = warp & 3;
-        int it = 0;
-        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
-            const int a = it & 1;
-            const int m0 = mb * BM;
-            mbar_wait(&acc_full[a], (it >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + q * 32 + lane;
-            float *crow = C + cmap.off(row < M ? row : 0) + n0;
-#pragma unroll 1
-            for (int cb = 0; cb < BN; cb += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * kAccCols + cb);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (row < M) store_row32(crow + cb, r, bias ? bias + n0 + cb : nullptr, relu, wide);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
-    }
-}
+constexpr int kMaxResChunks = 4;                     // K <= 128: the weight block fits the tensor-memory-resident kernel
 
 // =================================================================================================
 // K <= 128, WEIGHTS IN TENSOR MEMORY, transposed product.  D^T[feature][token] = W[feature][k] . X[token][k]:
@@ -747,133 +610,6 @@ __device__ __forceinline__ void tile_store_mn(const float4 (&v)[8], unsigned cha
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const float *__restrict__ dY, RowMap ymap,
-                                                                 const float *__restrict__ X, RowMap xmap, int T, int No, int Ni,
-                                                                 int nsplit, float *__restrict__ part_w,
-                                                                 float *__restrict__ part_b) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kStages * kStageBytes);
-    uint64_t *full = bars, *empty = bars + kStages, *acc_full = bars + 2 * kStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 4);
-    float *colsum_s = reinterpret_cast<float *>(bars + 2 * kStages + 6);        // [producer warps][128] floats
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
-    const int tile = blockIdx.x % tiles_mn, split = blockIdx.x / tiles_mn;
-    const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
-    const int chunks_total = (T + BK - 1) / BK;
-    const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 2 * kProducerThreads / 32); mbar_init(&empty[s], 1); }
-        mbar_init(&acc_full[0], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kAccCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < kMmaWarp) {
-        // ===== PRODUCERS =====  work item i = (chunk i/2, operand i%2: 0 = dY, 1 = X); group g takes i == g (mod groups)
-        // and keeps the next item's eight loads in flight while it splits the current one.
-        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
-        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool want_b = part_b != nullptr && n0 == 0;
-        const uint32_t total_items = 2u * (uint32_t)my_chunks;
-        auto load_item = [&](uint32_t i, float4 (&dst)[8]) {
-            const int t0 = (split + (int)(i >> 1) * nsplit) * BK;
-            if (i & 1) tile_load_mn(X, xmap, t0, T, n0, t, dst);
-            else tile_load_mn(dY, ymap, t0, T, m0, t, dst);
-        };
-        float4 v[8], vn[8];
-        uint32_t i = g;
-        if (i < total_items) load_item(i, v);
-        for (; i < total_items; i += kProducerGroups) {
-            if (i + kProducerGroups < total_items) load_item(i + kProducerGroups, vn);
-            const uint32_t j = i >> 1;
-            const int stage = j % kStages;
-            mbar_wait(&empty[stage], ((j / kStages) & 1) ^ 1);
-            unsigned char *st = tiles + (size_t)stage * kStageBytes + ((i & 1) ? 2 * kTileBytes : 0);
-            tile_store_mn(v, st, st + kTileBytes, t, (want_b && !(i & 1)) ? &cs : nullptr);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[stage]);            // one arrival per warp (128 single arrivals serialise on the barrier)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = vn[q];
-        }
-        if (want_b) *reinterpret_cast<float4 *>(colsum_s + warp * 128 + lane * 4) = cs;
-    } else if (warp == kMmaWarp) {
-        // ===== MMA ISSUER =====
-        for (int j = 0; j < my_chunks; ++j) {
-            const int stage = j % kStages;
-            mbar_wait(&full[stage], (j / kStages) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t base = smem_u32(tiles + (size_t)stage * kStageBytes);
-#pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {                          // 8 tokens = two 4-token groups per MMA
-                    const uint32_t adv = ks * 2 * kKGroupBytes;
-                    const uint64_t a_hi = make_desc_mn(base + adv), a_lo = make_desc_mn(base + kTileBytes + adv);
-                    const uint64_t b_hi = make_desc_mn(base + 2 * kTileBytes + adv), b_lo = make_desc_mn(base + 3 * kTileBytes + adv);
-                    const uint32_t first = (j | ks) != 0;
-                    umma_tf32(tmem_base, a_lo, b_hi, kIdescMN, first);
-                    umma_tf32(tmem_base, a_hi, b_lo, kIdescMN, 1u);
-                    umma_tf32(tmem_base, a_hi, b_hi, kIdescMN, 1u);
-                }
-                umma_commit(&empty[stage]);
-                if (j == my_chunks - 1) umma_commit(&acc_full[0]);
-            }
-            __syncwarp();
-        }
-    } else {
-        // ===== EPILOGUE: TMEM partial -> workspace [split][tile][128][128] =====
-        const int q = warp & 3;
-        float *prow = part_w + (((size_t)split * tiles_mn + tile) * BM + q * 32 + lane) * BN;
-        if (my_chunks > 0) {
-            mbar_wait(&acc_full[0], 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-#pragma unroll 1
-        for (int cb = 0; cb < BN; cb += 32) {
-            uint32_t r[32];
-            if (my_chunks > 0) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            store_row32(prow + cb, r, nullptr, 0, true);                      // workspace rows are 512-byte aligned
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (part_b != nullptr && n0 == 0 && threadIdx.x < 128) {         // column sums of this CTA's share of dY
-        float s = 0.f;
-        for (int w = 0; w < kMmaWarp; ++w) s += colsum_s[w * 128 + threadIdx.x];
-        part_b[(size_t)split * No + m0 + threadIdx.x] = s;
-    }
-    if (warp == kMmaWarp) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kAccCols));
-    }
-}
-
 // ---- weight gradient, dY^T as the A operand in TENSOR MEMORY ------------------------------------------------------------
 // ncu on gemm_wgrad_kernel: splitting BOTH operands through shared memory costs 64 KB of stores + 96 KB of tensor-core reads
 // per 32-token chunk (LSU shared wavefronts 27 % + tensor-core shared wavefronts 35 % + the global loads on the same L1 data
@@ -1122,44 +858,42 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
                "dc_gemm_tf32x3: leading dimensions must be >= extent and multiples of 4 floats");
     DC_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0 && (!bias || ((uintptr_t)bias & 15) == 0),
                DC_EINVAL, "dc_gemm_tf32x3: pointers must be 16-byte aligned");
-    static bool attr_set = false;
-    if (!attr_set) {
-        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_set = true;
-    }
     // 256-bit epilogue stores need 32-byte aligned rows
     const bool wide = ((uintptr_t)C & 31) == 0 && ldc % 8 == 0 && (cmap.rpb == 0 || cmap.bs % 8 == 0) &&
                       (!bias || ((uintptr_t)bias & 31) == 0);
     const int tiles = (int)((M + BM - 1) / BM) * (N / BN);
     const int n_blocks = N / BN, m_blocks = (int)((M + BM - 1) / BM);
-    if (K / BK <= kMaxResChunks && n_blocks <= dc_sm_count()) {          // resident-B specialisation
-        static bool attr_b = false;
-        if (!attr_b) {
-            DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_bres_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesBRes));
-            attr_b = true;
-        }
+    // the shared-memory opt-in is a per-device attribute: set it on every call (cheap) rather than caching it per process
+    if (K / BK <= kMaxResChunks && n_blocks <= dc_sm_count()) {          // K <= 128: weights resident in tensor memory
         int per_col = dc_sm_count() / n_blocks;                          // CTAs per column block
         if (per_col > m_blocks) per_col = m_blocks;
-        static int use_wtmem = -1;                                        // DC_GEMM_WTMEM=0: weights resident in shared memory instead
-        if (use_wtmem < 0) { const char *e = getenv("DC_GEMM_WTMEM"); use_wtmem = (e && e[0] == '0') ? 0 : 1; }
-        if (use_wtmem) {
-            static bool attr_t = false;
-            if (!attr_t) {
-                DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
-                attr_t = true;
-            }
-            gemm_tf32x3_wtmem_kernel<<<per_col * n_blocks, kThreads, kSmemBytesWTmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
-                                                                                                          (int)M, N, K, relu);
-            DC_LAUNCH_OK();
-            return DC_OK;
-        }
-        gemm_tf32x3_bres_kernel<<<per_col * n_blocks, kThreads, kSmemBytesBRes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
-                                                                                                       (int)M, N, K, relu, wide);
+        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
+        gemm_tf32x3_wtmem_kernel<<<per_col * n_blocks, kThreads, kSmemBytesWTmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
+                                                                                                      (int)M, N, K, relu);
         DC_LAUNCH_OK();
         return DC_OK;
     }
+    DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
-    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap, (int)M, N, K, relu, wide);
+    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap, (int)M, N, K, relu, wide, 1, 0);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+// Split-K form for the skinny products of the step-wise recurrence (csrc/rnn_stepwise.cuh): part[sp] = A[:, K range sp] *
+// B[:, K range sp]^T for sp < ksplit, each [M, N] with leading dimension N, `ksplit` chosen by the caller so that
+// tiles x ksplit fills the SMs.  Library-internal (C++ linkage).
+int dc_gemm_tf32x3_splitk(const float *A, int lda, const float *B, int ldb, float *part, int64_t M, int N, int K, int ksplit,
+                          bool first_call, cudaStream_t st) {
+    DC_REQUIRE(A && B && part && ksplit >= 1 && N % BN == 0 && K % (BK * ksplit) == 0 && M > 0, DC_EINVAL,
+               "dc_gemm_tf32x3_splitk: bad arguments (M=%lld N=%d K=%d ksplit=%d)", (long long)M, N, K, ksplit);
+    if (first_call)                                   // per-device attribute; the step loop calls this thousands of times
+        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    const int tiles = (int)((M + BM - 1) / BM) * (N / BN) * ksplit;
+    const int grid = tiles < dc_sm_count() ? tiles : dc_sm_count();
+    const bool wide = ((uintptr_t)part & 31) == 0 && N % 8 == 0 && ((size_t)M * N) % 8 == 0;
+    gemm_tf32x3_kernel<<<grid, kThreads, kSmemBytes, st>>>(A, make_rowmap(lda, 0, 0), B, ldb, nullptr, part, make_rowmap(N, 0, 0), (int)M,
+                                                            N, K, 0, wide, ksplit, (long long)M * N);
     DC_LAUNCH_OK();
     return DC_OK;
 }
@@ -1187,29 +921,12 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
     DC_REQUIRE(((uintptr_t)dY & 15) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)dW & 15) == 0 && ((uintptr_t)workspace & 15) == 0 &&
                    ((uintptr_t)db & 15) == 0,
                DC_EINVAL, "dc_gemm_wgrad_tf32x3: pointers must be 16-byte aligned");
-    const size_t smem = kSmemBytes + kMmaWarp * 128 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const int tiles_mn = (No / BM) * (Ni / BN), nsplit = wgrad_splits(No, Ni);
     float *part_w = reinterpret_cast<float *>(workspace);
     float *part_b = db ? part_w + (size_t)nsplit * No * Ni : nullptr;
     cudaStream_t st = dc_cu_stream(stream);
-    static int use_atmem = -1;                                        // DC_WGRAD_ATMEM=0: both operands through shared memory
-    if (use_atmem < 0) { const char *e = getenv("DC_WGRAD_ATMEM"); use_atmem = (e && e[0] == '0') ? 0 : 1; }
-    if (use_atmem) {
-        static bool attr_a = false;
-        if (!attr_a) {
-            DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
-            attr_a = true;
-        }
-        gemm_wgrad_atmem_kernel<<<tiles_mn * nsplit, kThreadsG, kSmemBytesWgradA, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w,
-                                                                                    part_b);
-    } else {
-        gemm_wgrad_kernel<<<tiles_mn * nsplit, kThreads, smem, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
-    }
+    DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
+    gemm_wgrad_atmem_kernel<<<tiles_mn * nsplit, kThreadsG, kSmemBytesWgradA, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
     DC_LAUNCH_OK();
     const int total4 = No * Ni / 4 + (db ? No / 4 : 0);
     wgrad_reduce_kernel<<<(total4 + 31) / 32, 32 * kRedRows, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);

@@ -413,12 +413,9 @@ extern "C" int dc_ppo_loss_fwd_bwd_strided(const float *const logits[DC_NUM_HEAD
     const unsigned blocks = (unsigned)((N + kTile - 1) / kTile);
     ppo_stats_kernel<<<blocks, kTile, 0, st>>>(hp, adv_raw, N, ws, n_actions);
     DC_LAUNCH_OK();
-    static bool attr_set = false;
-    if (!attr_set) {
-        DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_set = true;
-    }
+    // per-device attribute: set on every call (a process-wide "done" flag breaks the second GPU of a process)
+    DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     ppo_loss_kernel<false><<<blocks, kTile, kSmemBytes, st>>>(hp, old_logp, adv_raw, ret, value, N, e_clip,
                                                               entropy_coef, vf_coef, dvalue, out, ws, nullptr);
     DC_LAUNCH_OK();
@@ -447,11 +444,8 @@ extern "C" int dc_selected_logp(const float *const logits[DC_NUM_HEADS], const u
         hp.ld_l[h] = head_n(h); hp.ld_d[h] = head_n(h);
     }
     hp.ld_v = 1; hp.ld_dv = 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-        DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        attr_set = true;
-    }
+    // per-device attribute: set on every call (a process-wide "done" flag breaks the second GPU of a process)
+    DC_CUDA(cudaFuncSetAttribute(ppo_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     const unsigned blocks = (unsigned)((N + kTile - 1) / kTile);
     ppo_loss_kernel<true><<<blocks, kTile, kSmemBytes, dc_cu_stream(stream)>>>(
         hp, nullptr, nullptr, nullptr, nullptr, N, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, logp_out);

@@ -18,7 +18,10 @@
 //     L2-resident scratch (reduce-scatter, fixed summation order => deterministic);
 //   * gate math: thread = (unit, 4 sequences), 128-byte coalesced global accesses; the per-step global inputs are
 //     prefetched one step ahead into registers while the MMAs run.
-// Per step and CTA: 96 tcgen05.mma (M128 N32 K8) ~ 1.5k cycles, one cluster barrier, one L2 round trip.
+// Per step and CTA: 96 tcgen05.mma (M128 N32 K8), one cluster barrier, one L2 round trip.  ncu (profiles/r2_rnn_cluster_ncu.md):
+// a chain of MMAs into ONE accumulator is latency-bound (~100 cycles per dependent MMA vs ~30 of tensor-pipe work), so every
+// K-panel accumulates into its own TMEM accumulator (8 independent chains of 12) and the epilogue adds them; the cluster
+// barrier is split (arrive.release right after the exchanged slice is stored, wait.acquire after the remaining stores).
 // Algorithmic HBM bytes per token: forward 4*(G+1)*H, backward 8*(G+1)*H.
 #pragma once
 #include "dc_common.cuh"
@@ -28,7 +31,7 @@ namespace dc_rnnc {
 constexpr int kH = 256;
 constexpr int kCL = 8;                  // CTAs per cluster
 constexpr int kNB = 32;                 // sequences per cluster = MMA N
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kPanelA = 128 * 128;      // bytes of one A tile: 128 rows x 32 tf32 (one SWIZZLE_128B row each)
 constexpr int kPanelB = kNB * 128;      // bytes of one B tile:  32 rows x 32 tf32
 
@@ -79,6 +82,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -99,9 +107,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 // All threads of all CTAs of the cluster.  release/acquire at cluster scope: global writes made before the barrier by any
 // thread of the cluster are visible to every thread of the cluster after it.
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_barrier() { cluster_arrive(); cluster_wait(); }
 __device__ __forceinline__ unsigned char *align1024(unsigned char *p) {
     return reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
 }
@@ -127,7 +135,8 @@ __device__ __forceinline__ void tmem_free_512(uint32_t tmem_base, int warp) {
 }
 
 // ---- forward ------------------------------------------------------------------------------------------------------------
-// TMEM: [0,256) W_hh slice, hi half: lane rho = g*32 + u  <->  row g*H + 32*rank + u, column = k;  [256,288) accumulator.
+// TMEM: [0,256) W_hh slice, hi half: lane rho = g*32 + u  <->  row g*H + 32*rank + u, column = k;  [256,512) eight
+// accumulators of 32 columns, one per K-panel.
 // shared: W lo half (8 K-panels of [128 rows x 32]), h hi / lo (8 K-panels of [32 sequences x 32]), transposition scratch.
 struct FwdSmem {
     static constexpr size_t wlo = 0;
@@ -137,12 +146,13 @@ struct FwdSmem {
     static constexpr size_t bars = scratch + 4 * kNB * 32 * 4;
     static constexpr size_t total = bars + 64 + 1024;             // + alignment slack
 };
+constexpr int kNP = 2;                                            // (sequence, unit) pairs per thread in the gate phase
 
 template <int G>
 __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, const float *__restrict__ w_hh,
                                                                    const float *__restrict__ b_hh, float *ybuf, float *cbuf,
                                                                    int B, int S) {
-    constexpr int H = kH, GH = G * kH;
+    constexpr int H = kH, GH = G * kH, NP = kNP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = align1024(smem_raw);
     unsigned char *wlo = base + FwdSmem::wlo, *hhi = base + FwdSmem::hhi, *hlo = base + FwdSmem::hlo;
@@ -161,13 +171,13 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_w = tmem_base, tmem_acc = tmem_base + 256;
 
-    {   // resident weights, once: warp (q, khalf) fills lanes [32q, 32q+32), columns [128*khalf, 128*khalf+128)
-        const int q = warp & 3, khalf = warp >> 2, rho = q * 32 + lane;
+    {   // resident weights, once: warp (q, kq) fills lanes [32q, 32q+32), columns [64*kq, 64*kq+64)
+        const int q = warp & 3, kq = warp >> 2, rho = q * 32 + lane;
         const bool valid = q < G;                                          // q == gate index; GRU has no 4th gate: zero rows
         const float *wrow = w_hh + (size_t)(q * H + rank * 32 + lane) * H;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 #pragma unroll 2
-        for (int k0 = khalf * 128; k0 < khalf * 128 + 128; k0 += 8) {
+        for (int k0 = kq * 64; k0 < kq * 64 + 64; k0 += 8) {
             float w[8], hi[8], lo[8];
             if (valid) {
                 const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wrow + k0)), w1 = __ldg(reinterpret_cast<const float4 *>(wrow + k0 + 4));
@@ -191,23 +201,26 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // gate phase: thread = (unit ul, sequences sb + 8 i)
+    // gate phase: thread = (unit ul, sequences sb + 16 i)
     const int ul = lane, unit = rank * 32 + ul, sb = warp;
-    float bias[G], c_reg[4], h_reg[4], cur[4][G], nxt[4][G];
-    bool live[4];
+    float bias[G], c_reg[NP], h_reg[NP], cur[NP][G], nxt[NP][G];
+    bool live[NP];
 #pragma unroll
     for (int g = 0; g < G; ++g) bias[g] = __ldg(b_hh + g * H + unit);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int b = b0 + sb + 8 * i;
+    for (int i = 0; i < NP; ++i) {
+        const int b = b0 + sb + 16 * i;
         live[i] = b < B;
         c_reg[i] = (G == 4 && live[i]) ? cbuf[(size_t)b * H + unit] : 0.f;
         h_reg[i] = (G == 3 && live[i]) ? ybuf[(size_t)b * H + unit] : 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) cur[i][g] = live[i] ? gates[(size_t)b * GH + g * H + unit] : 0.f;
+        for (int g = 0; g < G; ++g) {
+            cur[i][g] = live[i] ? gates[(size_t)b * GH + g * H + unit] : 0.f;
+            nxt[i][g] = 0.f;
+        }
     }
-    // h-tile loader: thread = (sequence hb, 16-byte chunk hc) of every K-panel
-    const int hc = tid & 7, hb = tid >> 3;
+    // h-tile loader: thread = (sequence hb, 16-byte chunk hc) of K-panels hp0, hp0+2, hp0+4, hp0+6
+    const int hc = tid & 7, hb = (tid >> 3) & 31, hp0 = tid >> 8;
     const bool hlive = b0 + hb < B;
     cluster_barrier();
 
@@ -215,15 +228,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
         // ---- A: gather h_{t-1} [32 x 256] (ybuf slot t) from L2, split, store the B-operand tiles
         {
             const float *src = ybuf + ((size_t)t * B + b0 + hb) * H + 4 * hc;
-            float4 v[8];
+            float4 v[4];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) v[p] = hlive ? __ldcg(reinterpret_cast<const float4 *>(src + 32 * p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j)
+                v[j] = hlive ? __ldcg(reinterpret_cast<const float4 *>(src + 32 * (hp0 + 2 * j))) : make_float4(0.f, 0.f, 0.f, 0.f);
             const int off = swz(hb, hc);
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
+            for (int j = 0; j < 4; ++j) {
+                const int p = hp0 + 2 * j;
                 float4 hi, lo;
-                hi.x = tf32_rna(v[p].x); hi.y = tf32_rna(v[p].y); hi.z = tf32_rna(v[p].z); hi.w = tf32_rna(v[p].w);
-                lo.x = v[p].x - hi.x; lo.y = v[p].y - hi.y; lo.z = v[p].z - hi.z; lo.w = v[p].w - hi.w;
+                hi.x = tf32_rna(v[j].x); hi.y = tf32_rna(v[j].y); hi.z = tf32_rna(v[j].z); hi.w = tf32_rna(v[j].w);
+                lo.x = v[j].x - hi.x; lo.y = v[j].y - hi.y; lo.z = v[j].z - hi.z; lo.w = v[j].w - hi.w;
                 *reinterpret_cast<float4 *>(hhi + p * kPanelB + off) = hi;
                 *reinterpret_cast<float4 *>(hlo + p * kPanelB + off) = lo;
             }
@@ -231,86 +246,107 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // ---- B: 96 MMAs by one thread
+        // ---- B: 96 MMAs by one thread; K-panel p accumulates into its own accumulator (8 independent chains, issued
+        //      round-robin so that consecutive instructions never depend on each other)
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t wlo_a = smem_u32(wlo), hhi_a = smem_u32(hhi), hlo_a = smem_u32(hlo);
 #pragma unroll 1
-            for (int p = 0; p < 8; ++p) {
-                const uint64_t a_lo = make_desc(wlo_a + p * kPanelA), b_hi = make_desc(hhi_a + p * kPanelB), b_lo = make_desc(hlo_a + p * kPanelB);
+            for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t a_hi = tmem_w + p * 32 + ks * 8;
-                    umma_ss(tmem_acc, a_lo + 2 * ks, b_hi + 2 * ks, kIdesc, (p | ks) != 0);     // small terms first
-                    umma_ts(tmem_acc, a_hi, b_lo + 2 * ks, kIdesc, 1u);
-                    umma_ts(tmem_acc, a_hi, b_hi + 2 * ks, kIdesc, 1u);
-                }
+                for (int p = 0; p < 8; ++p)                                                      // small terms first
+                    umma_ss(tmem_acc + 32 * p, make_desc(wlo_a + p * kPanelA) + 2 * ks, make_desc(hhi_a + p * kPanelB) + 2 * ks, kIdesc, ks != 0);
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    umma_ts(tmem_acc + 32 * p, tmem_w + p * 32 + ks * 8, make_desc(hlo_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    umma_ts(tmem_acc + 32 * p, tmem_w + p * 32 + ks * 8, make_desc(hhi_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
             }
             umma_commit(mma_done);
         }
+        __syncwarp();
         // prefetch the next step's i2h pre-activations while the tensor core works
         if (t + 1 < S) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < NP; ++i)
 #pragma unroll
                 for (int g = 0; g < G; ++g)
-                    nxt[i][g] = live[i] ? gates[((size_t)(t + 1) * B + b0 + sb + 8 * i) * GH + g * H + unit] : 0.f;
+                    nxt[i][g] = live[i] ? gates[((size_t)(t + 1) * B + b0 + sb + 16 * i) * GH + g * H + unit] : 0.f;
         }
         mbar_wait(mma_done, t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- C: accumulator -> scratch [gate][sequence][unit] -> gate math
+        // ---- C: sum of the 8 accumulators -> scratch [gate][sequence][unit] -> gate math
         {
-            const int q = warp & 3, half = warp >> 2;
-            uint32_t r[16];
-            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + 16 * half, r);
+            const int q = warp & 3, cgp = warp >> 2;                               // TMEM lane quadrant (= gate), 8-column group
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 8 * cgp;
+            float sum[8];
+            uint32_t r[8];
+            tmem_ld8(taddr, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 16; ++j) scratch[(q * kNB + 16 * half + j) * 32 + lane] = __uint_as_float(r[j]);
+            for (int j = 0; j < 8; ++j) sum[j] = __uint_as_float(r[j]);
+#pragma unroll
+            for (int p = 1; p < 8; ++p) {
+                tmem_ld8(taddr + 32 * p, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum[j] += __uint_as_float(r[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) scratch[(q * kNB + 8 * cgp + j) * 32 + lane] = sum[j];
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        float act[NP][G + 1];                                                      // activated gates (+ c | hn) of this step
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int bb = sb + 8 * i;
+        for (int i = 0; i < NP; ++i) {
+            const int bb = sb + 16 * i;
             float pre[G];
 #pragma unroll
             for (int g = 0; g < G; ++g) pre[g] = bias[g] + scratch[(g * kNB + bb) * 32 + ul];
+            float hnew;
+            if (G == 3) {
+                const float r = dc_sigmoid(cur[i][0] + pre[0]);
+                const float z = dc_sigmoid(cur[i][1] + pre[1]);
+                const float n = dc_tanh(cur[i][2] + r * pre[2]);
+                hnew = (1.0f - z) * n + z * h_reg[i];
+                act[i][0] = r; act[i][1] = z; act[i][2] = n; act[i][G] = pre[2];   // W_hn h + b_hn -> cbuf slot t+1
+                h_reg[i] = hnew;
+            } else {
+                const float ig = dc_sigmoid(cur[i][0] + pre[0]);
+                const float fg = dc_sigmoid(cur[i][1] + pre[1]);
+                const float gg = dc_tanh(cur[i][2] + pre[2]);
+                const float og = dc_sigmoid(cur[i][G - 1] + pre[G - 1]);
+                c_reg[i] = fg * c_reg[i] + ig * gg;
+                hnew = og * dc_tanh(c_reg[i]);
+                act[i][0] = ig; act[i][1] = fg; act[i][2] = gg; act[i][G - 1] = og; act[i][G] = c_reg[i];
+            }
+            if (live[i]) ybuf[((size_t)(t + 1) * B + b0 + bb) * H + unit] = hnew;  // the slice the other CTAs wait for
+        }
+        // ---- D: publish this CTA's slice of h_t (release), then write the rest of the step's outputs behind the barrier
+        cluster_arrive();
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
             if (live[i]) {
-                const size_t tok = (size_t)t * B + b0 + bb;
+                const size_t tok = (size_t)t * B + b0 + sb + 16 * i;
                 float *gout = gates + tok * GH + unit;
-                float hnew;
-                if (G == 3) {
-                    const float r = dc_sigmoid(cur[i][0] + pre[0]);
-                    const float z = dc_sigmoid(cur[i][1] + pre[1]);
-                    const float n = dc_tanh(cur[i][2] + r * pre[2]);
-                    hnew = (1.0f - z) * n + z * h_reg[i];
-                    gout[0] = r; gout[H] = z; gout[2 * H] = n;
-                    cbuf[(tok + B) * H + unit] = pre[2];                           // W_hn h + b_hn, slot t+1
-                    h_reg[i] = hnew;
-                } else {
-                    const float ig = dc_sigmoid(cur[i][0] + pre[0]);
-                    const float fg = dc_sigmoid(cur[i][1] + pre[1]);
-                    const float gg = dc_tanh(cur[i][2] + pre[2]);
-                    const float og = dc_sigmoid(cur[i][G - 1] + pre[G - 1]);
-                    c_reg[i] = fg * c_reg[i] + ig * gg;
-                    hnew = og * dc_tanh(c_reg[i]);
-                    gout[0] = ig; gout[H] = fg; gout[2 * H] = gg; gout[(G - 1) * H] = og;
-                    cbuf[(tok + B) * H + unit] = c_reg[i];
-                }
-                ybuf[(tok + B) * H + unit] = hnew;
+#pragma unroll
+                for (int g = 0; g < G; ++g) gout[g * H] = act[i][g];
+                cbuf[(tok + B) * H + unit] = act[i][G];
             }
 #pragma unroll
             for (int g = 0; g < G; ++g) cur[i][g] = nxt[i][g];
         }
-        // ---- D: publish this CTA's slice of h_t to the cluster
-        cluster_barrier();
+        cluster_wait();
     }
     tmem_free_512(tmem_base, warp);
 }
 
 // ---- backward -----------------------------------------------------------------------------------------------------------
 // TMEM: [0,256) W_hh^T slice, hi half, two M tiles: tile m, lane rho <-> k = 128 m + rho, column kappa = g*32 + u <->
-// j = g*H + 32*rank + u;  [256,320) two accumulators.  shared: lo half (2 x 4 K-panels), gate-gradient tile hi / lo.
+// j = g*H + 32*rank + u;  [256,512) eight accumulators of 32 columns (M tile m, K-panel g at 256 + 32*(4m + g)).
+// shared: lo half (2 x 4 K-panels), gate-gradient tile hi / lo.
 struct BwdSmem {
     static constexpr size_t wlo = 0;
     static constexpr size_t ghi = wlo + 8 * kPanelA;
@@ -327,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
                                                                    const float *__restrict__ dhn, const float *__restrict__ dcn,
                                                                    float *__restrict__ dh0, float *__restrict__ dc0, float *part,
                                                                    int B, int S) {
-    constexpr int H = kH, GH = G * kH;
+    constexpr int H = kH, GH = G * kH, NP = kNP;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *base = align1024(smem_raw);
     unsigned char *wlo = base + BwdSmem::wlo, *ghi = base + BwdSmem::ghi, *glo = base + BwdSmem::glo;
@@ -345,12 +381,12 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_w = tmem_base, tmem_acc = tmem_base + 256;
 
-    const int q = warp & 3, mt = warp >> 2;                                // TMEM lane quadrant, M tile
+    const int q = warp & 3, mt = (warp >> 2) & 1, wh = warp >> 3;          // TMEM lane quadrant, M tile, half (K range / columns)
     {   // resident W_hh^T slice, once: lane rho of tile mt <-> k; a warp reads 32 consecutive k of one row j (128 B)
         const int rho = q * 32 + lane, k = mt * 128 + rho;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
 #pragma unroll 2
-        for (int kap0 = 0; kap0 < 128; kap0 += 8) {
+        for (int kap0 = wh * 64; kap0 < wh * 64 + 64; kap0 += 8) {
             float w[8], hi[8], lo[8];
             const int g = kap0 >> 5;
 #pragma unroll
@@ -371,16 +407,16 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // gate phase: thread = (unit ul, sequences sb + 8 i)
+    // gate phase: thread = (unit ul, sequences sb + 16 i)
     const int ul = lane, unit = rank * 32 + ul, sb = warp;
-    bool live[4];
-    float dh_carry[4], dc_carry[4], c_cur[4];
+    bool live[NP];
+    float dh_carry[NP], dc_carry[NP], c_cur[NP];
     // per-step inputs, prefetched one step ahead: saved gates, dy, aux0 (LSTM c_{t-1} | GRU hn), aux1 (GRU h_{t-1})
-    float cg[4][G], cdy[4], ca0[4], ca1[4], ng[4][G], ndy[4], na0[4], na1[4];
-    auto fetch = [&](int t, float (&fg)[4][G], float (&fdy)[4], float (&fa0)[4], float (&fa1)[4]) {
+    float cg[NP][G], cdy[NP], ca0[NP], ca1[NP], ng[NP][G], ndy[NP], na0[NP], na1[NP];
+    auto fetch = [&](int t, float (&fg)[NP][G], float (&fdy)[NP], float (&fa0)[NP], float (&fa1)[NP]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const size_t tok = (size_t)t * B + b0 + sb + 8 * i;
+        for (int i = 0; i < NP; ++i) {
+            const size_t tok = (size_t)t * B + b0 + sb + 16 * i;
             if (live[i]) {
 #pragma unroll
                 for (int g = 0; g < G; ++g) fg[i][g] = gates[tok * GH + g * H + unit];
@@ -400,23 +436,25 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
         }
     };
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int b = b0 + sb + 8 * i;
+    for (int i = 0; i < NP; ++i) {
+        const int b = b0 + sb + 16 * i;
         live[i] = b < B;
         dh_carry[i] = (live[i] && dhn) ? dhn[(size_t)b * H + unit] : 0.f;
         dc_carry[i] = (G == 4 && live[i] && dcn) ? dcn[(size_t)b * H + unit] : 0.f;
         c_cur[i] = (G == 4 && live[i]) ? cbuf[((size_t)S * B + b) * H + unit] : 0.f;
     }
     fetch(S - 1, cg, cdy, ca0, ca1);
+    fetch(S - 1, ng, ndy, na0, na1);                                               // (initialises the second buffer)
     cluster_barrier();
 
     for (int it = 0; it < S; ++it) {
         const int t = S - 1 - it;
         // ---- recurrent gradient: fixed-order sum of the 8 CTAs' partials of the previous step, then the gate gradients
         const float *pprev = part + ((size_t)(((it + 1) & 1) * ncl + cl) * kCL) * kNB * H;
+        float dgi[NP][G], daux[NP];                                                // global outputs of this step, stored behind the MMAs
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int bb = sb + 8 * i;
+        for (int i = 0; i < NP; ++i) {
+            const int bb = sb + 16 * i;
             float dh = cdy[i] + dh_carry[i];
             if (it > 0) {
                 float pv[kCL];
@@ -426,17 +464,18 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
                 for (int r = 0; r < kCL; ++r) dh += pv[r];
             }
             float d[4] = {0.f, 0.f, 0.f, 0.f};                                     // gradients wrt the h2h pre-activations
+#pragma unroll
+            for (int g = 0; g < G; ++g) dgi[i][g] = 0.f;
+            daux[i] = 0.f;
             if (live[i]) {
-                const size_t tok = (size_t)t * B + b0 + bb;
-                float *gout = gates + tok * GH + unit;
                 if (G == 3) {
                     const float r = cg[i][0], z = cg[i][1], n = cg[i][2], hn = ca0[i], hprev = ca1[i];
                     const float dpn = dh * (1.0f - z) * (1.0f - n * n);
                     const float dpz = dh * (hprev - n) * z * (1.0f - z);
                     const float dpr = dpn * hn * r * (1.0f - r);
                     const float dghn = dpn * r;
-                    gout[0] = dpr; gout[H] = dpz; gout[2 * H] = dpn;               // dgi
-                    cbuf[(tok + B) * H + unit] = dghn;                             // n-gate part of dgh
+                    dgi[i][0] = dpr; dgi[i][1] = dpz; dgi[i][2] = dpn;             // dgi
+                    daux[i] = dghn;                                                // n-gate part of dgh -> cbuf slot t+1
                     d[0] = dpr; d[1] = dpz; d[2] = dghn;
                     dh_carry[i] = dh * z;
                 } else {
@@ -447,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
                     const float dpf = dc * cprev * fg * (1.0f - fg);
                     const float dpg = dc * ig * (1.0f - gg * gg);
                     const float dpo = dh * tc * og * (1.0f - og);
-                    gout[0] = dpi; gout[H] = dpf; gout[2 * H] = dpg; gout[(G - 1) * H] = dpo;
+                    dgi[i][0] = dpi; dgi[i][1] = dpf; dgi[i][2] = dpg; dgi[i][G - 1] = dpo;
                     d[0] = dpi; d[1] = dpf; d[2] = dpg; d[3] = dpo;
                     dc_carry[i] = dc * fg;
                     c_cur[i] = cprev;
@@ -466,54 +505,79 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {                                                            // 2 x G independent chains, round-robin
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t wlo_a = smem_u32(wlo), ghi_a = smem_u32(ghi), glo_a = smem_u32(glo);
 #pragma unroll 1
-            for (int m = 0; m < 2; ++m) {
-#pragma unroll 1
-                for (int p = 0; p < G; ++p) {
-                    const uint64_t a_lo = make_desc(wlo_a + (m * 4 + p) * kPanelA), b_hi = make_desc(ghi_a + p * kPanelB),
-                                   b_lo = make_desc(glo_a + p * kPanelB);
+            for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint32_t a_hi = tmem_w + m * 128 + p * 32 + ks * 8;
-                        umma_ss(tmem_acc + 32 * m, a_lo + 2 * ks, b_hi + 2 * ks, kIdesc, (p | ks) != 0);
-                        umma_ts(tmem_acc + 32 * m, a_hi, b_lo + 2 * ks, kIdesc, 1u);
-                        umma_ts(tmem_acc + 32 * m, a_hi, b_hi + 2 * ks, kIdesc, 1u);
-                    }
+                for (int c = 0; c < 2 * G; ++c) {
+                    const int m = c / G, p = c % G;
+                    umma_ss(tmem_acc + 32 * (4 * m + p), make_desc(wlo_a + (m * 4 + p) * kPanelA) + 2 * ks, make_desc(ghi_a + p * kPanelB) + 2 * ks,
+                            kIdesc, ks != 0);
+                }
+#pragma unroll
+                for (int c = 0; c < 2 * G; ++c) {
+                    const int m = c / G, p = c % G;
+                    umma_ts(tmem_acc + 32 * (4 * m + p), tmem_w + m * 128 + p * 32 + ks * 8, make_desc(glo_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
+                }
+#pragma unroll
+                for (int c = 0; c < 2 * G; ++c) {
+                    const int m = c / G, p = c % G;
+                    umma_ts(tmem_acc + 32 * (4 * m + p), tmem_w + m * 128 + p * 32 + ks * 8, make_desc(ghi_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
                 }
             }
             umma_commit(mma_done);
         }
-        if (t > 0) fetch(t - 1, ng, ndy, na0, na1);                                // next step's inputs, behind the MMAs
+        __syncwarp();
+        // behind the MMAs: this step's global outputs, then the next step's inputs
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (!live[i]) continue;
+            const size_t tok = (size_t)t * B + b0 + sb + 16 * i;
+            float *gout = gates + tok * GH + unit;
+#pragma unroll
+            for (int g = 0; g < G; ++g) gout[g * H] = dgi[i][g];
+            if (G == 3) cbuf[(tok + B) * H + unit] = daux[i];
+        }
+        if (t > 0) fetch(t - 1, ng, ndy, na0, na1);
         mbar_wait(mma_done, it & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {   // partial dh_{t-1}[b][k] of this CTA's 128 gate columns -> scratch [buffer][cluster][rank][b][k]
-            uint32_t r[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + 32 * mt, r);
+            const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 32 * (4 * mt) + 16 * wh;
+            float sum[16];
+            uint32_t r[16];
+            tmem_ld16(taddr, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float *dst = part + (((size_t)((it & 1) * ncl + cl) * kCL + rank) * kNB) * H + mt * 128 + q * 32 + lane;
 #pragma unroll
-            for (int b = 0; b < kNB; ++b) __stcg(dst + (size_t)b * H, __uint_as_float(r[b]));
+            for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(r[j]);
+#pragma unroll
+            for (int p = 1; p < G; ++p) {
+                tmem_ld16(taddr + 32 * p, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(r[j]);
+            }
+            float *dst = part + (((size_t)((it & 1) * ncl + cl) * kCL + rank) * kNB + 16 * wh) * H + mt * 128 + q * 32 + lane;
+#pragma unroll
+            for (int b = 0; b < 16; ++b) __stcg(dst + (size_t)b * H, sum[b]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (t > 0) {
+        cluster_arrive();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NP; ++i) {
 #pragma unroll
-                for (int g = 0; g < G; ++g) cg[i][g] = ng[i][g];
-                cdy[i] = ndy[i]; ca0[i] = na0[i]; ca1[i] = na1[i];
-            }
+            for (int g = 0; g < G; ++g) cg[i][g] = ng[i][g];
+            cdy[i] = ndy[i]; ca0[i] = na0[i]; ca1[i] = na1[i];
         }
-        cluster_barrier();
+        cluster_wait();
     }
     // gradient of the initial state
     const float *plast = part + ((size_t)(((S - 1) & 1) * ncl + cl) * kCL) * kNB * H;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NP; ++i) {
         if (!live[i]) continue;
-        const int bb = sb + 8 * i;
+        const int bb = sb + 16 * i;
         float dh = dh_carry[i];
 #pragma unroll
         for (int r = 0; r < kCL; ++r) dh += __ldcg(plast + ((size_t)r * kNB + bb) * H + unit);

@@ -6,15 +6,18 @@
 #include "rnn_generic.cuh"
 #include "rnn_resident.cuh"
 #include "rnn_cluster.cuh"
+#include "rnn_stepwise.cuh"
 
 // Kernel selection by width (no environment switches, no library fallback):
 //   H == 128  rnn_resident.cuh  W_hh resident in registers + shared memory of ONE SM, packed-fp32 FFMA2
 //   H == 256  rnn_cluster.cuh   W_hh resident in tensor memory + shared memory of an 8-CTA cluster, tcgen05 3xTF32
-//   other H   rnn_generic.cuh   W_hh streamed from L2 every step (correct for any H % 4 == 0)
+//   H % 128 == 0 (384, 512, ...)  rnn_stepwise.cuh  per step: split-K tcgen05 3xTF32 GEMM over all SMs + gate kernel
+//   other H   rnn_generic.cuh   W_hh streamed from L2 every step, scalar FMA (correct for any H % 4 == 0)
 
 extern "C" size_t dc_rnn_workspace_bytes(int cell, int B, int H) {
     const int G = cell == DC_CELL_GRU ? 3 : 4;
     if (dc_rnnc::cluster_supported(H)) return dc_rnnc::bwd_workspace_bytes(B > 0 ? B : 1);   // partial-sum exchange (backward)
+    if (dc_rnns::stepwise_supported(H)) return dc_rnns::workspace_bytes(cell, B > 0 ? B : 1, H);
     return (size_t)G * H * H * sizeof(float);   // W_hh^T for the forward kernels that read the transpose
 }
 
@@ -33,6 +36,7 @@ extern "C" int dc_rnn_seq_fwd(int cell, float *gates, const float *w_hh, const f
     cudaStream_t st = dc_cu_stream(stream);
     const int G = cell == DC_CELL_GRU ? 3 : 4;
     if (dc_rnnc::cluster_supported(H)) return dc_rnnc::launch_fwd(cell, gates, w_hh, b_hh, ybuf, cbuf, B, S, st);   // reads W_hh as stored
+    if (dc_rnns::stepwise_supported(H)) return dc_rnns::launch_fwd(cell, gates, w_hh, b_hh, ybuf, cbuf, B, S, H, workspace, st);
     // the other forward kernels read W_hh^T [H, G*H] so that output columns are contiguous (coalesced / float4)
     float *wT = reinterpret_cast<float *>(workspace);
     dim3 tb(32, 8), tg((H + 31) / 32, (G * H + 31) / 32);
@@ -63,6 +67,10 @@ extern "C" int dc_rnn_seq_bwd(int cell, float *gates, const float *w_hh, const f
     if (dc_rnnc::cluster_supported(H)) {
         DC_REQUIRE(workspace, DC_EINVAL, "dc_rnn_seq_bwd: the H = 256 kernels need the workspace (dc_rnn_workspace_bytes)");
         return dc_rnnc::launch_bwd(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, reinterpret_cast<float *>(workspace), B, S, st);
+    }
+    if (dc_rnns::stepwise_supported(H)) {
+        DC_REQUIRE(workspace, DC_EINVAL, "dc_rnn_seq_bwd: the step-wise kernels need the workspace (dc_rnn_workspace_bytes)");
+        return dc_rnns::launch_bwd(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, H, workspace, st);
     }
     if (dc_rnn::resident_supported(cell, H))
         return dc_rnn::launch_bwd_resident(cell, gates, w_hh, ybuf, cbuf, dy, dhn, dcn, dh0, dc0, B, S, H, st);

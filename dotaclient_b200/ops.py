@@ -4,14 +4,10 @@ Every function here requires CUDA tensors and enqueues hand-written sm_100a kern
 ``libdotaclient_b200.so`` on torch's current stream.  No CPU path exists: CPU tensors raise.
 """
 import ctypes
-import os
 
 import torch
 
 from . import _lib
-
-# dense layers whose shape allows it run on the tcgen05 3xTF32 GEMM (fp32-level accuracy); "0" = library SGEMM only
-_TC_ENABLED = os.environ.get("DOTACLIENT_B200_TC_GEMM", "1") == "1"
 
 CELL_ID = {"gru": 0, "lstm": 1}
 HEAD_KEYS = ("enum", "x", "y", "target_unit", "ability")     # policy.py:46
@@ -151,28 +147,16 @@ def _rnn_workspace(cell, B, H, device):
     return ws
 
 
-def _i2h_matmul_context():
-    """The input-to-hidden GEMM is the one dense contraction that may use tensor cores (TF32)."""
-    return os.environ.get("DOTACLIENT_B200_I2H_TF32", "0") == "1"
-
-
 def _rnn_forward_impl(x, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
-    """i2h GEMM (cuBLAS) + recurrence kernel.  Returns (x2, w_ih, w_hh, gates, ybuf, cbuf)."""
+    """i2h GEMM (tcgen05 3xTF32, ``dc_gemm_tf32x3``) + recurrence kernel.  Returns (x2, w_ih, w_hh, gates, ybuf, cbuf)."""
     _need_cuda(x, w_ih, w_hh, b_ih, b_hh, h0, c0)
     S, B, Hin = x.shape
     H = w_hh.shape[1]
     N = S * B
     x2 = _f32c(x.detach()).view(N, Hin)
     w_ih, w_hh, b_ih, b_hh = _f32c(w_ih.detach()), _f32c(w_hh.detach()), _f32c(b_ih.detach()), _f32c(b_hh.detach())
-    if _TC_ENABLED and gemm_tf32x3_supported(N, w_ih.shape[0], Hin):
-        gates = gemm_tf32x3(x2, w_ih, b_ih)              # [N, G*H] = x W_ih^T + b_ih on tcgen05 (3xTF32)
-    else:
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = _i2h_matmul_context()
-        try:
-            gates = torch.addmm(b_ih, x2, w_ih.t())
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+    # [N, G*H] = x W_ih^T + b_ih on tcgen05 (3xTF32); shapes outside the kernel's (G*H % 128, Hin % 32) raise DC_EUNSUPPORTED
+    gates = gemm_tf32x3(x2, w_ih, b_ih)
     ybuf = torch.empty((S + 1, B, H), dtype=torch.float32, device=x.device)
     cbuf = torch.empty((S + 1, B, H), dtype=torch.float32, device=x.device)
     ybuf[0].copy_(h0.detach().reshape(B, H))
@@ -196,7 +180,7 @@ def rnn_forward_states(x_tm, w_ih, w_hh, b_ih, b_hh, h0, c0, cell):
 
 
 class RnnSequence(torch.autograd.Function):
-    """Time-major GRU/LSTM layer: i2h GEMM (cuBLAS) + hand-written recurrence kernels.
+    """Time-major GRU/LSTM layer: i2h GEMM (tcgen05 3xTF32) + hand-written recurrence kernels.
 
     forward(x [S,B,Hin], w_ih [G*H,Hin], w_hh [G*H,H], b_ih, b_hh, h0 [B,H], c0 [B,H]|None, cell)
       -> y [S,B,H], h_n [B,H], c_n [B,H] (zeros-size-0 tensor for GRU)
@@ -241,38 +225,17 @@ class RnnSequence(torch.autograd.Function):
                                           _lib.ptr(dc0), B, S, H, ws.data_ptr(), _lib.stream_ptr()), "dc_rnn_seq_bwd")
         dgi = gates                                   # [N, G*H], overwritten in place by the kernel
         hprev = ybuf[:S].view(N, H)                   # h_{t-1} for every token (slot t)
-        tf32 = _i2h_matmul_context()
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = tf32
-        try:
-            if not ctx.needs_input_grad[0]:
-                dx = None
-            elif _TC_ENABLED and gemm_tf32x3_supported(N, Hin, G * H):
-                dx = gemm_tf32x3(dgi, w_ih.t().contiguous()).view(S, B, Hin)     # dx = dgi W_ih on tcgen05
-            else:
-                dx = torch.mm(dgi, w_ih).view(S, B, Hin)
-            tc = gemm_wgrad_supported(N, G * H, Hin) and gemm_wgrad_supported(N, G * H, H) and H % 128 == 0
-            if tc:
-                dw_ih, db_ih = gemm_wgrad_tf32x3(dgi, x2)                         # dW_ih = dgi^T x, db_ih = colsum(dgi)
-            else:
-                dw_ih = torch.mm(dgi.t(), x2)
-                db_ih = dgi.sum(0)
-            if cell == "lstm":
-                dw_hh = gemm_wgrad_tf32x3(dgi, hprev, want_bias=False)[0] if tc else torch.mm(dgi.t(), hprev)
-                db_hh = db_ih
-            else:
-                dghn = cbuf[1:].view(N, H)            # n-gate part of dgh (= dgi_n * r)
-                dw_hh = torch.empty_like(w_hh)
-                if tc:
-                    gemm_wgrad_tf32x3(dgi[:, :2 * H], hprev, want_bias=False, dw_out=dw_hh[:2 * H])
-                    _, db_n = gemm_wgrad_tf32x3(dghn, hprev, dw_out=dw_hh[2 * H:])
-                else:
-                    torch.mm(dgi[:, :2 * H].t(), hprev, out=dw_hh[:2 * H])
-                    torch.mm(dghn.t(), hprev, out=dw_hh[2 * H:])
-                    db_n = dghn.sum(0)
-                db_hh = torch.cat([db_ih[:2 * H], db_n])
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
+        dx = gemm_tf32x3(dgi, w_ih.t().contiguous()).view(S, B, Hin) if ctx.needs_input_grad[0] else None   # dx = dgi W_ih
+        dw_ih, db_ih = gemm_wgrad_tf32x3(dgi, x2)                              # dW_ih = dgi^T x, db_ih = colsum(dgi)
+        if cell == "lstm":
+            dw_hh = gemm_wgrad_tf32x3(dgi, hprev, want_bias=False)[0]
+            db_hh = db_ih
+        else:
+            dghn = cbuf[1:].view(N, H)                # n-gate part of dgh (= dgi_n * r)
+            dw_hh = torch.empty_like(w_hh)
+            gemm_wgrad_tf32x3(dgi[:, :2 * H], hprev, want_bias=False, dw_out=dw_hh[:2 * H])
+            _, db_n = gemm_wgrad_tf32x3(dghn, hprev, dw_out=dw_hh[2 * H:])
+            db_hh = torch.cat([db_ih[:2 * H], db_n])
         return dx, dw_ih, dw_hh, db_ih, db_hh, dh0, dc0, None
 
 
@@ -376,16 +339,9 @@ def gemm_tf32x3(a, b, bias=None, relu=False, out=None):
     return out
 
 
-def _tc_ok(M, N, K):
-    return _TC_ENABLED and gemm_tf32x3_supported(M, N, K)
-
-
 class LinearTC(torch.autograd.Function):
-    """``y = x W^T + b`` (optionally ReLU) with forward and data-gradient on the tcgen05 3xTF32 GEMM.
-
-    The weight gradient ``dW = dy^T x`` contracts over the token dimension (both operands MN-major) and stays on the
-    library SGEMM for now; ``db`` is a column sum.
-    """
+    """``y = x W^T + b`` (optionally ReLU): forward, data gradient and weight gradient (+ bias gradient from the same pass
+    over ``dy``) all on the tcgen05 3xTF32 GEMMs.  No library GEMM: unsupported shapes raise ``DC_EUNSUPPORTED``."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, relu):
@@ -407,33 +363,24 @@ class LinearTC(torch.autograd.Function):
             dy2 = torch.ops.aten.threshold_backward(dy2, y, 0.0)
         dx = None
         if ctx.needs_input_grad[0]:
-            if _tc_ok(dy2.shape[0], K, N):
-                dx = gemm_tf32x3(dy2, w.t().contiguous())
-            else:
-                dx = dy2 @ w
-            dx = dx.view(*dy.shape[:-1], K)
-        if ctx.needs_input_grad[1] and gemm_wgrad_supported(dy2.shape[0], N, K):
+            dx = gemm_tf32x3(dy2, w.t().contiguous()).view(*dy.shape[:-1], K)
+        dw = db = None
+        if ctx.needs_input_grad[1]:
             dw, db = gemm_wgrad_tf32x3(dy2, x2, want_bias=ctx.has_bias)     # dW = dy^T x, db = colsum(dy), one pass over dy
-        else:
-            dw = torch.mm(dy2.t(), x2) if ctx.needs_input_grad[1] else None
-            db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db, None
 
 
 def linear(x, weight, bias=None, relu=False):
-    """Dense layer: tensor-core path when the shape allows (N % 128 == 0, K % 32 == 0), library SGEMM otherwise."""
-    M = x.numel() // x.shape[-1]
-    if x.is_cuda and _tc_ok(M, weight.shape[0], weight.shape[1]):
-        return LinearTC.apply(x, weight, bias, relu)
-    y = torch.nn.functional.linear(x, weight, bias)
-    return torch.relu(y) if relu else y
+    """Dense layer on the tcgen05 3xTF32 GEMM (out features % 128 == 0, in features % 32 == 0; CUDA tensors only)."""
+    _need_cuda(x, weight, bias)
+    return LinearTC.apply(x, weight, bias, relu)
 
 
 _wgrad_ws = {}
 
 
 def gemm_wgrad_supported(T, No, Ni):
-    return _TC_ENABLED and T > 0 and No % 128 == 0 and Ni % 128 == 0
+    return T > 0 and No % 128 == 0 and Ni % 128 == 0
 
 
 def gemm_wgrad_tf32x3(dy, x, want_bias=True, dw_out=None, db_out=None, accumulate=False):

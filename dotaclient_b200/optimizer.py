@@ -346,8 +346,9 @@ class DotaOptimizer:
         self.device = _device()
         _lib.load()                         # fail loudly, up front, if the CUDA library is missing
 
-        torch.manual_seed(7)                # :34 -- the reference seeds at import; Policy() init depends on it
-        self.policy_base = Policy(hidden_size=hidden_size, cell=cell)
+        with torch.random.fork_rng(devices=[]):     # :34 seeds torch with 7 at import and Policy() init depends on it;
+            torch.manual_seed(7)                    # forked so that constructing an optimizer leaves the caller's RNG alone
+            self.policy_base = Policy(hidden_size=hidden_size, cell=cell)
 
         if self.checkpoint:
             logger.info('Checkpointing to: {}'.format(self.log_dir))
@@ -382,12 +383,16 @@ class DotaOptimizer:
             if os.path.isfile(adam_file):
                 logger.info('Restoring Adam state from {}'.format(adam_file))
                 self.optimizer.load_state_dict(torch.load(adam_file, map_location='cpu'))
+        self._sync_resume_state()
         self._n_actions = torch.zeros(8, dtype=torch.int32, device=self.device)
         self._n_actions[VALUE_SLOT] = 1 if vf_coef > 0 else 0
         self._metrics = torch.zeros(4, dtype=torch.float32, device=self.device)
         self._finish_ws = torch.zeros(_lib.FINISH_WORKSPACE_BYTES, dtype=torch.uint8, device=self.device)
         self._host_result = torch.zeros(_lib.LOSS_SLOTS + 4, dtype=torch.float32).pin_memory()
         self.last_step_launch_estimate = 0
+        self._staging, self._staging_event = {}, None    # pinned host staging of the batched experience prep
+        self.use_cuda_graph = True          # replay device-resident batches of a known shape from a captured graph of the step
+        self._graphs = {}
         self.time_last_it = time.time()
 
         self.mq = mq if mq is not None else MessageQueue(host=self.rmq_host, port=self.rmq_port,
@@ -395,6 +400,20 @@ class DotaOptimizer:
                                                         use_model_exchange=self.checkpoint)
         self.mq.connect()
         self.upload_model(version=self.iteration_start)                  # :284
+
+    def _sync_resume_state(self):
+        """Data-parallel resume: only the master scans ``log_dir`` and restores (``checkpoint = is_master()``, :751), so the
+        restored Adam moments, step counters and ``iteration_start`` are broadcast from rank 0 -- otherwise the replicas
+        would apply different Adam updates to the same all-reduced gradient and silently diverge.  (The weights themselves
+        are broadcast by the wrapper's ``sync_parameters``, distributed.py:71-74.)"""
+        if not is_distributed():
+            return
+        dist.broadcast(self.exp_avg, 0)
+        dist.broadcast(self.exp_avg_sq, 0)
+        dist.broadcast(self.adam_steps, 0)
+        it = torch.tensor([self.iteration_start], dtype=torch.int64, device=self.device)
+        dist.broadcast(it, 0)
+        self.iteration_start = int(it.item())
 
     # -- checkpoints (:287-308, :697-723) --------------------------------------------------------
     @staticmethod
@@ -508,19 +527,31 @@ class DotaOptimizer:
         Lmax = max(Lps)
         same = all(L == Lmax for L in Ls)
 
-        def batched(group, key, dtype):
-            if same:                                                                   # no padding anywhere: one stack
-                host = np.stack([np.asarray(d[group][key]) for d in datas], axis=1).astype(dtype, copy=False)
-            else:
-                first = np.asarray(datas[0][group][key])
-                host = np.zeros((Lmax, R) + tuple(first.shape[1:]), dtype=dtype)       # zero padding (:367-382)
-                for i, d in enumerate(datas):
-                    host[:Ls[i], i] = np.asarray(d[group][key])
-            return torch.from_numpy(host).to(dev, non_blocking=True)
+        if self._staging_event is not None:
+            self._staging_event.synchronize()          # the previous iteration's uploads have left the staging buffers
 
-        obs = {k: batched('observations', k, np.float32) for k in Policy.INPUT_KEYS}
-        masks = {k: batched('masks', k, np.bool_) for k in Policy.OUTPUT_KEYS}
-        actions = {k: batched('actions', k, np.bool_) for k in Policy.OUTPUT_KEYS}
+        def batched(group, key, dtype):
+            """Rollouts -> one time-major ``[Lmax, R, ...]`` tensor, stacked straight into a cached PINNED staging buffer
+            (multi-threaded host copy) and uploaded asynchronously."""
+            srcs = [torch.as_tensor(d[group][key]) for d in datas]
+            shape = (Lmax, R) + tuple(srcs[0].shape[1:])
+            buf = self._staging.get((group, key))
+            if buf is None or buf.shape != shape or buf.dtype != dtype:
+                buf = torch.empty(shape, dtype=dtype).pin_memory()
+                self._staging[(group, key)] = buf
+            if same:                                                                   # no padding anywhere: one stack
+                torch.stack([t.to(dtype) for t in srcs], dim=1, out=buf)
+            else:
+                buf.zero_()                                                            # zero padding (:367-382)
+                for i, t in enumerate(srcs):
+                    buf[:Ls[i], i].copy_(t)
+            return buf.to(dev, non_blocking=True)
+
+        obs = {k: batched('observations', k, torch.float32) for k in Policy.INPUT_KEYS}
+        masks = {k: batched('masks', k, torch.bool) for k in Policy.OUTPUT_KEYS}
+        actions = {k: batched('actions', k, torch.bool) for k in Policy.OUTPUT_KEYS}
+        self._staging_event = torch.cuda.Event()
+        self._staging_event.record()
         rewards_np = np.zeros((R, Lmax, len(REWARD_KEYS)), dtype=np.float32)
         for i, d in enumerate(datas):
             rewards_np[i, :Ls[i]] = np.asarray(d['rewards'], dtype=np.float32)
@@ -601,13 +632,38 @@ class DotaOptimizer:
         """One PPO/Adam step on a list of ``Sequence`` (or an ``ExperienceBatch``).
 
         Returns the reference's three dicts: losses, per-head entropies, grad norms (CPU scalars).
+        A device-resident batch of a shape seen before is replayed from a CUDA graph of the whole step (forward, loss,
+        backward, all-reduce, finish: ~80 kernel launches -> one graph launch); batches still in flight from the host
+        (``prefetch``) run the same kernels launch by launch so that the upload overlaps them.
         """
         if isinstance(experiences, ExperienceBatch):
             batch = experiences if experiences.advantages.is_cuda else experiences.to(self.device)
         else:
             batch = ExperienceBatch.from_sequences(experiences, self.device)
-        keys = ops.HEAD_KEYS
         t_enter = time.perf_counter()
+        if self.use_cuda_graph and not ops.H2D_EVENTS and not ops.PROFILE.enabled:
+            out, metrics = self._replay_step(batch)
+        else:
+            out, metrics = self._enqueue_step(batch)
+        host = self._host_result
+        host[:_lib.LOSS_SLOTS].copy_(out, non_blocking=True)
+        host[_lib.LOSS_SLOTS:].copy_(metrics, non_blocking=True)
+        self.host_enqueue_s = time.perf_counter() - t_enter   # host time to launch the step (the GPU runs behind it)
+        torch.cuda.current_stream().synchronize()      # the step's single host sync (result read-back)
+        res = host.clone()
+        keys = ops.HEAD_KEYS
+        if res[_lib.LOSS_SLOTS + 3] != 0:               # :667-669, :678-679 (parameters were left untouched)
+            if math.isnan(float(res[0])):
+                raise ValueError('loss={}, policy_loss={}, entropy_loss={}, value_loss={}'.format(
+                    float(res[0]), float(res[1]), float(res[2]), float(res[3])))
+            raise ValueError('grad_norm={}'.format(float(res[_lib.LOSS_SLOTS])))
+        losses = {'loss': res[0], 'policy_loss': res[1], 'entropy_loss': res[2], 'value_loss': res[3]}
+        entropies = {k: res[4 + h] for h, k in enumerate(keys)}
+        return losses, entropies, {'unclipped': res[_lib.LOSS_SLOTS], 'clipped': res[_lib.LOSS_SLOTS + 1]}
+
+    def _enqueue_step(self, batch):
+        """Launches one optimizer step (:581-689) on the current stream; returns the device result vectors (loss slots, metrics)."""
+        keys = ops.HEAD_KEYS
         self.flat.zero_grad_detached()                                    # :671 (grads gathered into the flat buffer below)
         hidden = (batch.h0, batch.c0) if self.policy_base.cell == "lstm" else batch.h0
         ddp = self.policy if isinstance(self.policy, DistributedDataParallelSparseParamCPU) else None
@@ -617,20 +673,12 @@ class DotaOptimizer:
         logits, values, _ = self.policy.forward_time_major(batch.observations, hidden)   # :619
         ops.wait_h2d(batch.old_logp, batch.advantages, batch.returns, *batch.masks.values(), *batch.actions.values(),
                      *batch.observations.values())
-        packed = getattr(self.policy_base, "_packed_heads", None)
-        if packed is not None:          # small heads + value are column ranges of one packed GEMM output
-            out, n_actions, d_packed, d_tu = ops.ppo_loss_packed(
-                packed, logits['target_unit'], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
-                batch.old_logp, batch.advantages, batch.returns, self.e_clip, self.entropy_coef, self.vf_coef)
-            self._n_actions[:5].copy_(n_actions)
-            torch.autograd.backward([packed, logits['target_unit']], [d_packed, d_tu])                     # :672
-        else:
-            out, n_actions, dlogits, dvalue = ops.ppo_loss_fwd_bwd(
-                [logits[k] for k in keys], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
-                batch.old_logp, batch.advantages, batch.returns, values, self.e_clip, self.entropy_coef, self.vf_coef)
-            self._n_actions[:5].copy_(n_actions)
-            torch.autograd.backward([logits[k] for k in keys] + [values],
-                                    [g.view_as(logits[k]) for g, k in zip(dlogits, keys)] + [dvalue.view_as(values)])  # :672
+        packed = self.policy_base._packed_heads     # small heads + value are column ranges of one packed GEMM output
+        out, n_actions, d_packed, d_tu = ops.ppo_loss_packed(
+            packed, logits['target_unit'], [batch.masks[k] for k in keys], [batch.actions[k] for k in keys],
+            batch.old_logp, batch.advantages, batch.returns, self.e_clip, self.entropy_coef, self.vf_coef)
+        self._n_actions[:5].copy_(n_actions)
+        torch.autograd.backward([packed, logits['target_unit']], [d_packed, d_tu])                     # :672
         self.flat.gather_grads()
         # distributed.py:29-57 -> flags + ONE all-reduce; divide fused into the finish kernel
         ops.grad_flags(self.flat.grad_full, self.flat.total, self.flat.seg_head, self._n_actions)
@@ -641,20 +689,52 @@ class DotaOptimizer:
         ops.grad_finish(self.flat.param, self.flat.grad_full, self.exp_avg, self.exp_avg_sq, self.adam_steps,
                         self.flat.seg_lo, self.flat.seg_hi, self.flat.seg_head, self.flat.total, self.learning_rate, self.ADAM_BETAS,
                         self.ADAM_EPS, self.MAX_GRAD_NORM, out, self._metrics, self._finish_ws)     # :674-681
-        host = self._host_result
-        host[:_lib.LOSS_SLOTS].copy_(out, non_blocking=True)
-        host[_lib.LOSS_SLOTS:].copy_(self._metrics, non_blocking=True)
-        self.host_enqueue_s = time.perf_counter() - t_enter   # host time to launch the step (the GPU runs behind it)
-        torch.cuda.current_stream().synchronize()      # the step's single host sync (result read-back)
-        res = host.clone()
-        if res[_lib.LOSS_SLOTS + 3] != 0:               # :667-669, :678-679 (parameters were left untouched)
-            if math.isnan(float(res[0])):
-                raise ValueError('loss={}, policy_loss={}, entropy_loss={}, value_loss={}'.format(
-                    float(res[0]), float(res[1]), float(res[2]), float(res[3])))
-            raise ValueError('grad_norm={}'.format(float(res[_lib.LOSS_SLOTS])))
-        losses = {'loss': res[0], 'policy_loss': res[1], 'entropy_loss': res[2], 'value_loss': res[3]}
-        entropies = {k: res[4 + h] for h, k in enumerate(keys)}
-        return losses, entropies, {'unclipped': res[_lib.LOSS_SLOTS], 'clipped': res[_lib.LOSS_SLOTS + 1]}
+        return out, self._metrics
+
+    # -- CUDA graph of the step ----------------------------------------------------------------------
+    def _replay_step(self, batch):
+        """Replays the captured step for this batch shape (captures it the second time the shape is seen: the first call of
+        a shape runs launch by launch, which also warms every kernel up).  Inputs are copied into the graph's static
+        buffers (device to device); parameters, gradients, Adam state and step counters are the same device buffers the
+        eager path uses, so eager and graphed steps can be mixed freely."""
+        key = (batch.seq_len, batch.batch_size)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "seen"
+            return self._enqueue_step(batch)
+        if entry == "seen":
+            entry = self._capture_step(batch)
+            self._graphs[key] = entry
+            if entry == "eager":
+                return self._enqueue_step(batch)
+        elif entry == "eager":
+            return self._enqueue_step(batch)
+        static, graph, out = entry
+        srcs = [v for _, _, v in batch.tensors()]
+        dsts = [v for _, _, v in static.tensors()]
+        torch._foreach_copy_(dsts, srcs)
+        graph.replay()
+        return out, self._metrics
+
+    def _capture_step(self, batch):
+        static = ExperienceBatch({}, {}, {}, None, None, None, None, None)
+        for holder, k, v in batch.tensors():
+            c = v.detach().clone()
+            if isinstance(holder, dict):
+                (static.observations if holder is batch.observations else static.masks if holder is batch.masks else static.actions)[k] = c
+            else:
+                setattr(static, k, c)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                out, _ = self._enqueue_step(static)
+        except Exception as e:                      # same kernels either way: fall back to launch-by-launch for this shape
+            logger.warning('CUDA graph capture of the step failed (%s); this shape keeps running launch by launch', e)
+            torch.cuda.synchronize()
+            self.flat.rebind()
+            return "eager"
+        return static, graph, out
 
     def prefetch(self, experiences):
         """Starts the asynchronous upload of a pinned-host ``ExperienceBatch`` on the copy stream and returns the device batch

@@ -14,7 +14,6 @@ import logging
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import encoder_ops, ops
 
@@ -116,25 +115,13 @@ class Policy(nn.Module):
 
     # ------------------------------------------------------------------ implementation
     def _encode(self, env, groups):
-        """Observation encoders (``policy.py:97-138``) -> (x ``[..., H]``, unit embedding ``[..., 40, 128]``)."""
-        if ops._TC_ENABLED and env.is_cuda:
-            # explicit kernel chain (csrc/encoder.cu + tcgen05 GEMMs): no torch.cat, sparse max-pool backward
-            layers = [getattr(self, "affine_unit_" + s) for s, _, _ in UNIT_GROUPS]
-            unit_embedding, x = encoder_ops.unit_encoder(
-                env, self.affine_env.weight, self.affine_env.bias,
-                self.affine_unit_basic_stats.weight, self.affine_unit_basic_stats.bias, list(groups),
-                [l.weight for l in layers], [l.bias for l in layers])
-            return ops.linear(x, self.affine_pre_rnn.weight, self.affine_pre_rnn.bias, relu=True), unit_embedding
-        emb, emb_max = {}, {}
-        for (suffix, _, _), units in zip(UNIT_GROUPS, groups):
-            basic = F.relu(self.affine_unit_basic_stats(units))
-            layer = getattr(self, "affine_unit_" + suffix)
-            emb[suffix] = ops.linear(basic, layer.weight, layer.bias)          # tcgen05 3xTF32 GEMM
-            emb_max[suffix] = emb[suffix].max(dim=-2)[0]
-        # policy.py:127 takes the enemy-tower max from the enemy-NONHERO embedding; parity requires it.
-        emb_max["eth"] = emb_max["enh"]
-        unit_embedding = torch.cat([emb[s] for s, _, _ in UNIT_GROUPS], dim=-2)
-        x = torch.cat([F.relu(self.affine_env(env))] + [emb_max[s] for s, _, _ in UNIT_GROUPS], dim=-1)
+        """Observation encoders (``policy.py:97-138``) -> (x ``[..., H]``, unit embedding ``[..., 40, 128]``): the explicit
+        kernel chain of ``csrc/encoder.cu`` + tcgen05 GEMMs (no ``torch.cat``, sparse max-pool backward)."""
+        layers = [getattr(self, "affine_unit_" + s) for s, _, _ in UNIT_GROUPS]
+        unit_embedding, x = encoder_ops.unit_encoder(
+            env, self.affine_env.weight, self.affine_env.bias,
+            self.affine_unit_basic_stats.weight, self.affine_unit_basic_stats.bias, list(groups),
+            [l.weight for l in layers], [l.bias for l in layers])
         return ops.linear(x, self.affine_pre_rnn.weight, self.affine_pre_rnn.bias, relu=True), unit_embedding
 
     def _recur(self, x_tm, hidden):
@@ -149,34 +136,22 @@ class Policy(nn.Module):
         return y, new_hidden
 
     def _heads(self, y, unit_embedding):
-        """Action heads + value (``policy.py:144-155``).  Creation order as the reference's."""
-        attention = ops.linear(y, self.affine_unit_attention.weight, self.affine_unit_attention.bias).unsqueeze(-2)
+        """Action heads + value (``policy.py:144-155``): the attention projection and ONE packed ``[*, 128]`` tensor-core GEMM
+        for the four small heads + the value head (26 real rows, zero padding; their logits are column ranges of its
+        output, ``ops.PACK_COLS``), then the target-unit dot products."""
+        attention = ops.linear(y, self.affine_unit_attention.weight, self.affine_unit_attention.bias)
         H = self.hidden_size
-        if ops._TC_ENABLED and y.is_cuda and ops.gemm_tf32x3_supported(y.numel() // H, ops.PACK_WIDTH, H):
-            # the four small heads + the value head as ONE [*, 128] tensor-core GEMM (26 real rows, zero padding):
-            # their logits are column ranges of its output (ops.PACK_COLS)
-            pad = y.new_zeros(ops.PACK_WIDTH - 26, H)
-            w_pack = torch.cat([self.affine_head_enum.weight, self.affine_move_x.weight, self.affine_move_y.weight,
-                                self.affine_head_ability.weight, self.affine_value.weight, pad], dim=0)
-            b_pack = torch.cat([self.affine_head_enum.bias, self.affine_move_x.bias, self.affine_move_y.bias,
-                                self.affine_head_ability.bias, self.affine_value.bias, pad[:, 0]], dim=0)
-            packed = ops.linear(y, w_pack, b_pack)
-            self._packed_heads = packed                      # DotaOptimizer.train feeds gradients to it directly
-            cols = ops.PACK_COLS
-            head_enum, move_x, move_y, ability, value = (packed[..., cols[k][0]:cols[k][1]]
-                                                         for k in ("enum", "x", "y", "ability", "value"))
-            target_unit = encoder_ops.target_unit(attention.squeeze(-2), unit_embedding)
-            return {'enum': head_enum, 'x': move_x, 'y': move_y, 'target_unit': target_unit, 'ability': ability}, value
-        self._packed_heads = None
-        move_x = self.affine_move_x(y)
-        move_y = self.affine_move_y(y)
-        head_enum = self.affine_head_enum(y)
-        if ops._TC_ENABLED and y.is_cuda:
-            target_unit = encoder_ops.target_unit(attention.squeeze(-2), unit_embedding)
-        else:
-            target_unit = torch.matmul(attention, unit_embedding.transpose(-1, -2)).squeeze(-2)
-        ability = self.affine_head_ability(y)
-        value = self.affine_value(y)
+        pad = y.new_zeros(ops.PACK_WIDTH - 26, H)
+        w_pack = torch.cat([self.affine_head_enum.weight, self.affine_move_x.weight, self.affine_move_y.weight,
+                            self.affine_head_ability.weight, self.affine_value.weight, pad], dim=0)
+        b_pack = torch.cat([self.affine_head_enum.bias, self.affine_move_x.bias, self.affine_move_y.bias,
+                            self.affine_head_ability.bias, self.affine_value.bias, pad[:, 0]], dim=0)
+        packed = ops.linear(y, w_pack, b_pack)
+        self._packed_heads = packed                      # DotaOptimizer.train feeds gradients to it directly
+        cols = ops.PACK_COLS
+        head_enum, move_x, move_y, ability, value = (packed[..., cols[k][0]:cols[k][1]]
+                                                     for k in ("enum", "x", "y", "ability", "value"))
+        target_unit = encoder_ops.target_unit(attention, unit_embedding)
         return {'enum': head_enum, 'x': move_x, 'y': move_y, 'target_unit': target_unit, 'ability': ability}, value
 
     def _run(self, obs, hidden, time_major):
@@ -234,6 +209,23 @@ class Policy(nn.Module):
             u = torch.rand(A, 5, device=dev)
         chosen, logp = ops.select_actions([heads_logits[k] for k in ops.HEAD_KEYS], [masks[k] for k in ops.HEAD_KEYS], u.to(dev))
         return {k: chosen[:, h] for h, k in enumerate(ops.HEAD_KEYS)}, logp
+
+    def act_batched(self, hidden, observations, masks, u=None):
+        """One environment step for a POOL of ``A`` agents in one pass (the actor side of ``agent.py:578-674`` for many agents
+        at once): ``Policy.single`` for every agent as ONE ``[1, A]`` time-major forward -- batch-``A``
+        recurrence and heads on the same kernels as the optimizer -- followed by the hierarchical masked sampling kernel
+        (``select_actions_batched``, one launch for the pool).
+
+        ``hidden``: ``[1, A, H]`` (``(h, c)`` for the LSTM); ``observations``: ``{key: [A, ...]}`` (what ``single`` takes, with
+        a leading agent dimension); ``masks``: ``{head: [A, n]}`` legal-action masks (``action_masks``); ``u``: optional
+        ``[A, 5]`` uniforms.  Returns ``(chosen {head: int32 [A], -1 = not sampled}, logp [A, 5], logits {head: [A, n]},
+        value [A], new hidden)``.  Index selection is bit-exact against ``oracle.ref_policy.sample_index``."""
+        with torch.no_grad():
+            obs = {k: v.unsqueeze(0) for k, v in observations.items()}              # [1 (time), A, ...]
+            logits, value, new_hidden = self.forward_time_major(obs, hidden)
+            flat = {k: v[0] for k, v in logits.items()}
+            chosen, logp = self.select_actions_batched(flat, masks, u)
+        return chosen, logp, flat, value[0, :, 0], new_hidden
 
     @classmethod
     def head_masks(cls, selections):

@@ -332,6 +332,112 @@ def test_optimizer_step_vs_oracle(H, cell, S, tmp_path):
     assert float((dm - do).abs().max()) <= 3 * 2 * 5e-5 + 1e-6
 
 
+def _adam_state_by_name(oracle):
+    names = [n for n, _ in oracle.policy_base.named_parameters()]
+    out = {}
+    for n, p in zip(names, oracle.policy_base.parameters()):
+        st = oracle.optimizer.state.get(p)
+        if st:
+            out[n] = st
+    return out
+
+
+@pytest.mark.parametrize("H,cell,S,B", [(128, "lstm", 512, 8), (128, "lstm", 64, 1), (256, "gru", 64, 1), (256, "lstm", 128, 40)])
+def test_optimizer_step_long_bptt_vs_oracle(H, cell, S, B, tmp_path):
+    """Whole train() steps at BASELINE sequence lengths: C2's S = 512 (B = 8 keeps the CPU oracle at ~1 s/step), C1 (B = 1,
+    S = 64, at the widths of both the named LSTM-128 and the reference's GRU-256), and an H = 256 batch wide enough for the
+    cluster kernels (two clusters, one partly filled).  Error growth through S-step BPTT INSIDE the step is what is
+    tested: losses, entropies, gradient norms, per-tensor gradient direction, and after two steps torch.optim.Adam's own
+    state (step, exp_avg, exp_avg_sq) -- SURVEY.md 8(c) asks for moments, not only post-step weights."""
+    torch.set_num_threads(8)
+    mine = make_optimizer(H, cell, S, tmp_path)
+    oracle = make_oracle(H, cell, S)
+    rollouts = [make_rollout(S, 900 + 10 * H + i) for i in range(B)]
+    xs_m = [s for grp in mine.experiences_from_rollouts(copy.deepcopy(rollouts)) for s in grp]
+    xs_o = [s for r in rollouts for s in oracle.experiences_from_rollout(copy.deepcopy(r))]
+    _compare_sequences(xs_m, xs_o, cell)
+    for ep in range(2):
+        lm, em, gm = mine.train(xs_m)
+        lo, eo, go = oracle.train(xs_o)
+        for k in lo:
+            np.testing.assert_allclose(float(lm[k]), float(lo[k]), rtol=2e-4, atol=2e-6, err_msg="%s ep%d" % (k, ep))
+        for k in eo:
+            np.testing.assert_allclose(float(em[k]), float(eo[k]), rtol=2e-4, atol=1e-6, err_msg="entropy %s" % k)
+        np.testing.assert_allclose(float(gm["unclipped"]), float(go["unclipped"]), rtol=2e-3)
+        np.testing.assert_allclose(float(gm["clipped"]), float(go["clipped"]), rtol=2e-3)
+        if ep == 0:
+            for name, p in oracle.policy_base.named_parameters():
+                g = mine.flat.grad_of(name).cpu()
+                cos = torch.nn.functional.cosine_similarity(g.flatten(), p.grad.flatten(), dim=0)
+                assert cos > 0.9999, (name, float(cos))
+                np.testing.assert_allclose(float(g.norm()), float(p.grad.norm()), rtol=2e-3, err_msg=name)
+    # Adam state after two steps, tensor by tensor, in torch.optim.Adam's own layout
+    sd = mine.optimizer.state_dict()["state"]
+    want = _adam_state_by_name(oracle)
+    names = [n for n, _ in oracle.policy_base.named_parameters()]
+    assert sorted(names[i] for i in sd) == sorted(want)
+    for i, st in sd.items():
+        w = want[names[i]]
+        assert float(st["step"]) == float(w["step"]) == 2.0
+        m_scale = float(w["exp_avg"].abs().max())
+        v_scale = float(w["exp_avg_sq"].abs().max())
+        torch.testing.assert_close(st["exp_avg"], w["exp_avg"], rtol=2e-3, atol=2e-3 * m_scale + 1e-12)
+        torch.testing.assert_close(st["exp_avg_sq"], w["exp_avg_sq"], rtol=4e-3, atol=4e-3 * v_scale + 1e-20)
+        cos = torch.nn.functional.cosine_similarity(st["exp_avg"].flatten(), w["exp_avg"].flatten(), dim=0)
+        assert cos > 0.9999, (names[i], float(cos))
+
+
+def test_batch_from_rollouts_equals_stacked_sequences(tmp_path):
+    """The one-chunk fast path of batch_from_rollouts == ExperienceBatch.from_sequences over experiences_from_rollout."""
+    from dotaclient_b200.optimizer import ExperienceBatch
+    S = 16
+    mine = make_optimizer(128, "lstm", S, tmp_path)
+    rollouts = [make_rollout(S, 70 + i) for i in range(5)]
+    fast = mine.batch_from_rollouts(copy.deepcopy(rollouts))
+    slow = ExperienceBatch.from_sequences([s for r in rollouts for s in mine.experiences_from_rollout(copy.deepcopy(r))], dev())
+    for (_, ka, a), (_, kb, b) in zip(fast.tensors(), slow.tensors()):
+        assert ka == kb and a.shape == b.shape, (ka, a.shape, b.shape)
+        if a.dtype == torch.bool or ka in ("h0", "c0"):
+            assert torch.equal(a, b), ka
+        else:
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=ka)
+    ragged = [make_rollout(L, 80 + i) for i, L in enumerate((S, 2 * S + 3, S - 5))]
+    general = mine.batch_from_rollouts(copy.deepcopy(ragged))
+    assert general.batch_size == 1 + 3 + 1 and general.seq_len == S
+
+
+@pytest.mark.parametrize("H,cell", [(256, "gru"), (128, "lstm")])
+def test_policy_single_and_sequence_on_cuda(H, cell, tmp_path):
+    """Policy.init_hidden / sequence / single (policy.py:77-90) with CUDA tensors: an actor stepping one observation at a
+    time through .single() reproduces the hidden-state chain and the logits of one .sequence() call, and both match the
+    oracle (this is the actor-side use of the same kernels, batch 1)."""
+    mine = make_optimizer(H, cell, 8, tmp_path).policy_base
+    oracle = make_oracle(H, cell, 8).policy_base
+    d = dev()
+    r = make_rollout(6, 31)
+    obs = r["observations"]
+
+    def to_d(h):
+        return tuple(x.to(d) for x in h) if isinstance(h, tuple) else h.to(d)
+    with torch.no_grad():
+        lo, vo, ho = oracle.sequence(hidden=oracle.init_hidden(), **{k: v.clone() for k, v in obs.items()})
+        lm, vm, hm = mine.sequence(hidden=to_d(mine.init_hidden()), **{k: v.to(d) for k, v in obs.items()})
+        for k in HEADS:
+            assert lm[k].shape == lo[k].shape == (1, 6, dict(zip(HEADS, SIZES))[k])
+            torch.testing.assert_close(lm[k].cpu(), lo[k], rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(vm.cpu(), vo, rtol=1e-4, atol=2e-5)
+        h = to_d(mine.init_hidden())
+        for t in range(6):
+            lt, vt, h = mine.single(hidden=h, **{k: v[t].to(d) for k, v in obs.items()})
+            for k in HEADS:
+                assert lt[k].shape[:2] == (1, 1)
+                torch.testing.assert_close(lt[k][0, 0].cpu(), lo[k][0, t], rtol=1e-4, atol=3e-5)
+            torch.testing.assert_close(vt[0, 0].cpu(), vo[0, t], rtol=1e-4, atol=3e-5)
+        for a, b in zip(h if isinstance(h, tuple) else (h,), ho if isinstance(ho, tuple) else (ho,)):
+            assert a.shape == b.shape
+            torch.testing.assert_close(a.cpu(), b, rtol=1e-4, atol=3e-5)
+
+
 def test_unused_head_leaves_sparse_params_untouched(tmp_path):
     """No attack action in the batch -> affine_unit_attention / affine_unit_eth get no gradient: Adam must skip them
     and the grad-norm mean must exclude them (optimizer.py:627-630,693)."""
@@ -415,6 +521,44 @@ def test_policy_forward_batch_first_api_matches_time_major(tmp_path):
     torch.testing.assert_close(vm.cpu(), vo, rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(hm.cpu(), hn, rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(cm.cpu(), cn, rtol=1e-4, atol=2e-5)
+
+
+def test_act_batched_pool_matches_per_agent_single(tmp_path):
+    """Actor pool step: A agents through ONE batched forward + ONE selection launch == each agent's own
+    Policy.single() on the oracle followed by the pinned index function; two consecutive steps so the carried hidden state
+    is exercised."""
+    from oracle.ref_policy import sample_index
+    H, cell, A = 256, "gru", 37
+    mine = make_optimizer(H, cell, 8, tmp_path).policy_base
+    oracle = make_oracle(H, cell, 8).policy_base
+    d = dev()
+    g = torch.Generator().manual_seed(5)
+    rolls = [make_rollout(2, 600 + a) for a in range(A)]
+    hid_m = torch.zeros(1, A, H, device=d)
+    hid_o = [oracle.init_hidden() for _ in range(A)]
+    for t in range(2):
+        obs = {k: torch.stack([r["observations"][k][t] for r in rolls]) for k in mine.INPUT_KEYS}
+        masks = {k: torch.rand(A, n, generator=g) < 0.7 for k, n in zip(HEADS, SIZES)}
+        for k in masks:
+            masks[k][:, 1 if k == "target_unit" else 0] = True
+        u = torch.rand(A, 5, generator=g)
+        chosen, logp, logits, value, hid_m = mine.act_batched(hid_m, {k: v.to(d) for k, v in obs.items()},
+                                                              {k: v.to(d) for k, v in masks.items()}, u.to(d))
+        follow = {0: (), 1: ("x", "y"), 2: ("target_unit",), 3: ("ability",)}
+        for a in range(A):
+            with torch.no_grad():
+                lo, vo, hid_o[a] = oracle.sequence(hidden=hid_o[a], **{k: v[a:a + 1] for k, v in obs.items()})
+            for k in HEADS:
+                torch.testing.assert_close(logits[k][a].cpu(), lo[k][0, 0], rtol=1e-4, atol=3e-5)
+            torch.testing.assert_close(value[a].cpu(), vo[0, 0, 0], rtol=1e-4, atol=3e-5)
+            e = sample_index(logits["enum"][a].cpu(), masks["enum"][a], float(u[a, 0]))      # the index function on OUR logits: bit-exact
+            assert int(chosen["enum"][a]) == e
+            for h, k in enumerate(HEADS):
+                if k == "enum":
+                    continue
+                want = sample_index(logits[k][a].cpu(), masks[k][a], float(u[a, h])) if k in follow[e] else -1
+                assert int(chosen[k][a]) == want, (t, a, k)
+        torch.testing.assert_close(hid_m[0].cpu(), torch.cat([h[0] for h in hid_o]), rtol=1e-4, atol=3e-5)
 
 
 def test_cpu_tensors_are_rejected_loudly():
