@@ -259,7 +259,7 @@ def run_stream(args, cfg):
     opt = DotaOptimizer(rmq_host="stream", rmq_port=rank, epochs=epochs, min_seq_per_epoch=cfg["batch"], seq_len=cfg["seq_len"],
                         learning_rate=5e-5, checkpoint=False, pretrained_model=None, mq_prefetch_count=1,
                         log_dir=tempfile.mkdtemp(), entropy_coef=5e-4, vf_coef=0.5, run_local=True,
-                        hidden_size=cfg["hidden"], cell=cfg["cell"])
+                        hidden_size=cfg["hidden"], cell=cfg["cell"], rollout_prefetch=16)
     agents = max(1, 40 // world)
     rng = random.Random(7 + rank)
     pool = [pickle.dumps(make_rollout(rng.randint(1000, 1400), 7 + 1000 * rank + i, with_canvas=True)) for i in range(8)]

@@ -2,9 +2,10 @@
 
 Keeps the reference's module surface (``DotaOptimizer``, ``Sequence``, ``MessageQueue``,
 ``advantage_returns``, ``discount``, ``init_distribution``, ``main``, the CLI flags) while one
-optimizer step runs as:  fused unit encoder / cuBLAS GEMMs -> hand-written recurrence kernels ->
+optimizer step runs as:  unit-encoder kernel chain + tcgen05 3xTF32 GEMMs -> hand-written recurrence kernels ->
 fused PPO loss+grad kernel -> autograd backward through the same kernels -> ONE NCCL all-reduce of
-a flat gradient buffer -> fused count-divide / grad-norm / clip / Adam kernel.  CUDA only.
+a flat gradient buffer -> fused count-divide / grad-norm / clip / Adam kernel -- replayed from a CUDA graph
+when the batch is device-resident.  CUDA only.
 
 Line references are to TimZaman/dotaclient ``optimizer.py`` @ 8615b90.
 """
@@ -327,7 +328,8 @@ class DotaOptimizer:
 
     def __init__(self, rmq_host, rmq_port, epochs, min_seq_per_epoch, seq_len,
                  learning_rate, checkpoint, pretrained_model, mq_prefetch_count, log_dir,
-                 entropy_coef, vf_coef, run_local, *, hidden_size=256, cell="gru", mq=None, iterations=100000):
+                 entropy_coef, vf_coef, run_local, *, hidden_size=256, cell="gru", mq=None, iterations=100000,
+                 rollout_prefetch=0):
         self.rmq_host, self.rmq_port = rmq_host, rmq_port
         self.epochs = epochs
         self.min_seq_per_epoch = min_seq_per_epoch
@@ -391,6 +393,10 @@ class DotaOptimizer:
         self._host_result = torch.zeros(_lib.LOSS_SLOTS + 4, dtype=torch.float32).pin_memory()
         self.last_step_launch_estimate = 0
         self._staging, self._staging_event = {}, None    # pinned host staging of the batched experience prep
+        # rollout_prefetch > 0: a background thread pulls and unpickles up to that many rollouts ahead (same order, same
+        # rollouts as the reference's one-at-a-time loop, :448-466) while the GPU trains on the current iteration
+        self.rollout_prefetch = int(rollout_prefetch)
+        self._rollout_q, self._prefetch_thread = None, None
         self.use_cuda_graph = True          # replay device-resident batches of a known shape from a captured graph of the step
         self._graphs = {}
         self.time_last_it = time.time()
@@ -450,6 +456,20 @@ class DotaOptimizer:
         rollout_len = data['rewards'].shape[0]
         subrewards = data['rewards'].sum(axis=0)
         return data, subrewards, rollout_len, data['weight_version'], data.get('canvas')
+
+    def _next_rollout(self):
+        """``get_rollout()``, optionally served by the decode-ahead thread."""
+        if self.rollout_prefetch <= 0:
+            return self.get_rollout()
+        if self._prefetch_thread is None:
+            self._rollout_q = queue.Queue(maxsize=self.rollout_prefetch)
+
+            def pump():
+                while True:
+                    self._rollout_q.put(self.get_rollout())
+            self._prefetch_thread = threading.Thread(target=pump, daemon=True, name="dc-rollout-decode")
+            self._prefetch_thread.start()
+        return self._rollout_q.get()
 
     def experiences_from_rollout(self, data):
         """Rollout -> list of ``Sequence`` (:328-430), in ONE padded pass instead of a per-chunk loop.
@@ -770,7 +790,7 @@ class DotaOptimizer:
         rollouts, n_seq = [], 0
         while n_seq < self.min_seq_per_epoch:                             # :448
             start_xp_wait = time.time()
-            rollout, rollout_subrewards, rollout_len, weight_version, _ = self.get_rollout()
+            rollout, rollout_subrewards, rollout_len, weight_version, _ = self._next_rollout()
             xp_waits += time.time() - start_xp_wait
             rollouts.append(rollout)
             n_seq += (rollout_len + self.seq_len - 1) // self.seq_len
