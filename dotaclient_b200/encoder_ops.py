@@ -53,10 +53,9 @@ def _wgrad_workspace(No, Ni, device):
 
 # The unit embedding has two gradient sources: the target-unit head (rank-1, arrives first in backward) and the max-pool
 # (arrives with the pre-rnn gradient, after the recurrence).  When the embedding was produced by UnitEncoder, TargetUnit
-# does not materialise its [N,40,128] gradient: it parks (dlogits, attention) here and UnitEncoder.backward writes the
+# does not materialise its [N,40,128] gradient: it parks (dlogits, attention) in the `link` cell the two Functions of one
+# graph share (created by unit_encoder(), carried by the embedding tensor as `_dc_link`) and UnitEncoder.backward writes the
 # sum of both sources in ONE dense pass (dc_unit_grad_assemble).
-_UE_FROM_ENCODER = set()
-_PENDING_TU = {}
 
 
 def _ptr(t, float_offset=0):
@@ -71,8 +70,9 @@ class UnitEncoder(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, env, w_e, b_e, w_b, b_b, *rest):
+    def forward(ctx, link, env, w_e, b_e, w_b, b_b, *rest):
         units, weights, biases = rest[:6], rest[6:12], rest[12:18]
+        ctx.link = link
         _need_cuda(env, w_b, *units)
         lib = _lib.load()
         st = _lib.stream_ptr()
@@ -112,13 +112,7 @@ class UnitEncoder(torch.autograd.Function):
             basics.append(basic)
         ctx.N = N
         ctx.lead = lead
-        ctx.ue_ptr = ue.data_ptr()
         ctx.set_materialize_grads(False)               # an absent d_ue must arrive as None, not as 2.7 GB of zeros
-        if any(ctx.needs_input_grad):
-            if len(_UE_FROM_ENCODER) > 64:
-                _UE_FROM_ENCODER.clear()
-                _PENDING_TU.clear()
-            _UE_FROM_ENCODER.add(ctx.ue_ptr)
         ctx.save_for_backward(argmax, *units, *basics, *weights, env2, xcat)
         return ue.view(*lead, MAX_UNITS, C), xcat.view(*lead, XCAT)
 
@@ -130,8 +124,7 @@ class UnitEncoder(torch.autograd.Function):
         lib = _lib.load()
         st = _lib.stream_ptr()
         dev = argmax.device
-        pending = _PENDING_TU.pop(ctx.ue_ptr, None)
-        _UE_FROM_ENCODER.discard(ctx.ue_ptr)
+        pending = ctx.link.pop("pending", None)
         dw_e = db_e = None
         d_xm = None                                    # the maxima part of d_xcat, addressed in place (row pitch 896)
         if d_xcat is not None:
@@ -152,6 +145,9 @@ class UnitEncoder(torch.autograd.Function):
                                                      d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
         else:
             d_ue = _f32c(d_ue).reshape(N, MAX_UNITS, C)          # modified in place below (sole consumer)
+            if pending is not None:                               # the embedding had another consumer besides the deferred head:
+                dl, att = pending                                 # add the head's rank-1 part instead of losing it
+                d_ue = torch.addcmul(d_ue, dl.unsqueeze(-1), att.unsqueeze(1))
             if d_xm is not None:
                 for g in range(5):
                     copy = d_xm + 4 * 5 * C if g == 3 else None
@@ -181,14 +177,14 @@ class UnitEncoder(torch.autograd.Function):
                                                  db_b.data_ptr(), R, 1 if g > 0 else 0, ws_b.data_ptr(), st), "dc_unit_basic_bwd")
             dws.append(dw)
             dbs.append(db)
-        return (None, dw_e, db_e, dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
+        return (None, None, dw_e, db_e, dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
 
 
 class TargetUnit(torch.autograd.Function):
     """``logits[..., u] = <attention[..., :], unit_embedding[..., u, :]>`` (``policy.py:152-153``)."""
 
     @staticmethod
-    def forward(ctx, att, ue):
+    def forward(ctx, att, ue, link):
         _need_cuda(att, ue)
         lead = att.shape[:-1]
         N = att.numel() // C
@@ -199,7 +195,7 @@ class TargetUnit(torch.autograd.Function):
                        "dc_target_unit_fwd")
         ctx.save_for_backward(att2, ue2)
         ctx.shapes = (att.shape, ue.shape)
-        ctx.deferred = ue2.data_ptr() in _UE_FROM_ENCODER
+        ctx.link = link                                 # not None: the embedding comes from UnitEncoder, defer its gradient
         return logits.view(*lead, MAX_UNITS)
 
     @staticmethod
@@ -208,24 +204,29 @@ class TargetUnit(torch.autograd.Function):
         N = att2.shape[0]
         dl = _f32c(dlogits).reshape(N, MAX_UNITS)
         d_att = torch.empty_like(att2)
-        d_ue = None if ctx.deferred else torch.empty_like(ue2)
+        deferred = ctx.link is not None
+        d_ue = None if deferred else torch.empty_like(ue2)
         with PROFILE.span("target_unit_bwd", 1):       # bytes depend on how many tokens used the head (others are skipped)
             _lib.check(_lib.load().dc_target_unit_bwd(dl.data_ptr(), att2.data_ptr(), ue2.data_ptr(), d_att.data_ptr(),
                                                       None if d_ue is None else d_ue.data_ptr(), N, _lib.stream_ptr()),
                        "dc_target_unit_bwd")
-        if ctx.deferred:
-            _PENDING_TU[ue2.data_ptr()] = (dl, att2)            # consumed by UnitEncoder.backward
-            return d_att.view(ctx.shapes[0]), None
-        return d_att.view(ctx.shapes[0]), d_ue.view(ctx.shapes[1])
+        if deferred:
+            ctx.link["pending"] = (dl, att2)                    # consumed by UnitEncoder.backward
+            return d_att.view(ctx.shapes[0]), None, None
+        return d_att.view(ctx.shapes[0]), d_ue.view(ctx.shapes[1]), None
 
 
 def unit_encoder(env, w_e, b_e, w_b, b_b, units, weights, biases):
     """-> (unit embedding ``[..., 40, 128]``, pre-rnn input ``[..., 896]``)."""
-    return UnitEncoder.apply(env, w_e, b_e, w_b, b_b, *units, *weights, *biases)
+    link = {}
+    ue, xcat = UnitEncoder.apply(link, env, w_e, b_e, w_b, b_b, *units, *weights, *biases)
+    if ue.requires_grad:
+        ue._dc_link = link                              # lets target_unit() hand its gradient to this encoder's backward
+    return ue, xcat
 
 
 def target_unit(att, ue):
-    return TargetUnit.apply(att, ue)
+    return TargetUnit.apply(att, ue, getattr(ue, "_dc_link", None))
 
 
 __all__ = ["unit_encoder", "target_unit", "gemm_wgrad_supported"]

@@ -213,6 +213,12 @@ class ExperienceBatch:
         self.observations, self.masks, self.actions = observations, masks, actions
         self.old_logp, self.advantages, self.returns, self.h0, self.c0 = old_logp, advantages, returns, h0, c0
 
+    def __del__(self):
+        # a batch that was uploaded (prefetched) but never trained on must not leave its ready-events behind: a later tensor
+        # allocated at the same address would otherwise match a stale event
+        for ptr in getattr(self, "_h2d_ptrs", ()):
+            ops.H2D_EVENTS.pop(ptr, None)
+
     @property
     def seq_len(self):
         return self.advantages.shape[0]
@@ -252,6 +258,7 @@ class ExperienceBatch:
                 return 1
             return 100
         items = sorted(self.tensors(), key=priority)
+        out._h2d_ptrs = []
         for holder, k, v in items:
             if overlap:
                 with torch.cuda.stream(side):
@@ -260,6 +267,7 @@ class ExperienceBatch:
                     ev.record(side)
                 moved.record_stream(compute)
                 ops.H2D_EVENTS[moved.data_ptr()] = ev
+                out._h2d_ptrs.append(moved.data_ptr())
             else:
                 moved = v.to(device, non_blocking=non_blocking)
             if isinstance(holder, dict):
