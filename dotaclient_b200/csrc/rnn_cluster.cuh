@@ -20,8 +20,10 @@
 //     prefetched one step ahead into registers while the MMAs run.
 // Per step and CTA: 96 tcgen05.mma (M128 N32 K8), one cluster barrier, one L2 round trip.  ncu (profiles/r2_rnn_cluster_ncu.md):
 // a chain of MMAs into ONE accumulator is latency-bound (~100 cycles per dependent MMA vs ~30 of tensor-pipe work), so every
-// K-panel accumulates into its own TMEM accumulator (8 independent chains of 12) and the epilogue adds them; the cluster
-// barrier is split (arrive.release right after the exchanged slice is stored, wait.acquire after the remaining stores).
+// K-panel accumulates into its own TMEM accumulator (8 independent chains of 12) and the epilogue adds them; ONE thread issuing
+// all 96 MMAs is itself a bottleneck (~100 cycles of scalar work per instruction), so eight threads issue one chain each from
+// register-resident descriptors; the cluster barrier is split (arrive.release right after the exchanged slice is stored,
+// wait.acquire after the remaining stores).
 // Algorithmic HBM bytes per token: forward 4*(G+1)*H, backward 8*(G+1)*H.
 #pragma once
 #include "dc_common.cuh"
@@ -164,12 +166,19 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
     const int rank = blockIdx.x % kCL, b0 = (blockIdx.x / kCL) * kNB;
 
     if (tid == 0) {
-        mbar_init(mma_done, 1);
+        mbar_init(mma_done, 8);                                           // one commit per issuing thread
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tmem_alloc_512(tmem_slot, warp);
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_w = tmem_base, tmem_acc = tmem_base + 256;
+    // MMA issue: lane 0 of warp p issues the 12 MMAs of K-panel p into accumulator p.  ncu (v2): ONE thread issuing all 96 MMAs
+    // of a step needs ~100 cycles of scalar work per instruction (descriptor arithmetic, R2UR moves) for ~30 cycles of
+    // tensor-pipe work; eight threads issue concurrently and keep their (step-invariant) descriptors in registers.
+    const bool issuer = lane == 0 && warp < 8;
+    const uint64_t d_alo = make_desc(smem_u32(wlo) + (warp & 7) * kPanelA), d_bhi = make_desc(smem_u32(hhi) + (warp & 7) * kPanelB),
+                   d_blo = make_desc(smem_u32(hlo) + (warp & 7) * kPanelB);
+    const uint32_t t_acc = tmem_acc + 32 * (warp & 7), t_ahi = tmem_w + 32 * (warp & 7);
 
     {   // resident weights, once: warp (q, kq) fills lanes [32q, 32q+32), columns [64*kq, 64*kq+64)
         const int q = warp & 3, kq = warp >> 2, rho = q * 32 + lane;
@@ -246,22 +255,14 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // ---- B: 96 MMAs by one thread; K-panel p accumulates into its own accumulator (8 independent chains, issued
-        //      round-robin so that consecutive instructions never depend on each other)
-        if (tid == 0) {
+        // ---- B: 96 MMAs, 12 per issuing thread (K-panel = accumulator = warp index)
+        if (issuer) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t wlo_a = smem_u32(wlo), hhi_a = smem_u32(hhi), hlo_a = smem_u32(hlo);
-#pragma unroll 1
+#pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-                for (int p = 0; p < 8; ++p)                                                      // small terms first
-                    umma_ss(tmem_acc + 32 * p, make_desc(wlo_a + p * kPanelA) + 2 * ks, make_desc(hhi_a + p * kPanelB) + 2 * ks, kIdesc, ks != 0);
-#pragma unroll
-                for (int p = 0; p < 8; ++p)
-                    umma_ts(tmem_acc + 32 * p, tmem_w + p * 32 + ks * 8, make_desc(hlo_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
-#pragma unroll
-                for (int p = 0; p < 8; ++p)
-                    umma_ts(tmem_acc + 32 * p, tmem_w + p * 32 + ks * 8, make_desc(hhi_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
+                umma_ss(t_acc, d_alo + 2 * ks, d_bhi + 2 * ks, kIdesc, ks != 0);                 // small terms first
+                umma_ts(t_acc, t_ahi + 8 * ks, d_blo + 2 * ks, kIdesc, 1u);
+                umma_ts(t_acc, t_ahi + 8 * ks, d_bhi + 2 * ks, kIdesc, 1u);
             }
             umma_commit(mma_done);
         }
@@ -374,12 +375,18 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
     const int rank = blockIdx.x % kCL, cl = blockIdx.x / kCL, ncl = gridDim.x / kCL, b0 = cl * kNB;
 
     if (tid == 0) {
-        mbar_init(mma_done, 1);
+        mbar_init(mma_done, 2 * G);                                       // one commit per issuing thread
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tmem_alloc_512(tmem_slot, warp);
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_w = tmem_base, tmem_acc = tmem_base + 256;
+    // MMA issue: lane 0 of warp c < 2G issues the 12 MMAs of chain c = (M tile c / G, K-panel c % G) (see the forward kernel)
+    const bool issuer = lane == 0 && warp < 2 * G;
+    const int im = (warp % (2 * G)) / G, ip = (warp % (2 * G)) % G;
+    const uint64_t d_alo = make_desc(smem_u32(wlo) + (im * 4 + ip) * kPanelA), d_bhi = make_desc(smem_u32(ghi) + ip * kPanelB),
+                   d_blo = make_desc(smem_u32(glo) + ip * kPanelB);
+    const uint32_t t_acc = tmem_acc + 32 * (4 * im + ip), t_ahi = tmem_w + im * 128 + ip * 32;
 
     const int q = warp & 3, mt = (warp >> 2) & 1, wh = warp >> 3;          // TMEM lane quadrant, M tile, half (K range / columns)
     {   // resident W_hh^T slice, once: lane rho of tile mt <-> k; a warp reads 32 consecutive k of one row j (128 B)
@@ -505,27 +512,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {                                                            // 2 x G independent chains, round-robin
+        if (issuer) {                                                              // 2 x G chains of 12, one issuing thread each
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t wlo_a = smem_u32(wlo), ghi_a = smem_u32(ghi), glo_a = smem_u32(glo);
-#pragma unroll 1
+#pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-                for (int c = 0; c < 2 * G; ++c) {
-                    const int m = c / G, p = c % G;
-                    umma_ss(tmem_acc + 32 * (4 * m + p), make_desc(wlo_a + (m * 4 + p) * kPanelA) + 2 * ks, make_desc(ghi_a + p * kPanelB) + 2 * ks,
-                            kIdesc, ks != 0);
-                }
-#pragma unroll
-                for (int c = 0; c < 2 * G; ++c) {
-                    const int m = c / G, p = c % G;
-                    umma_ts(tmem_acc + 32 * (4 * m + p), tmem_w + m * 128 + p * 32 + ks * 8, make_desc(glo_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
-                }
-#pragma unroll
-                for (int c = 0; c < 2 * G; ++c) {
-                    const int m = c / G, p = c % G;
-                    umma_ts(tmem_acc + 32 * (4 * m + p), tmem_w + m * 128 + p * 32 + ks * 8, make_desc(ghi_a + p * kPanelB) + 2 * ks, kIdesc, 1u);
-                }
+                umma_ss(t_acc, d_alo + 2 * ks, d_bhi + 2 * ks, kIdesc, ks != 0);
+                umma_ts(t_acc, t_ahi + 8 * ks, d_blo + 2 * ks, kIdesc, 1u);
+                umma_ts(t_acc, t_ahi + 8 * ks, d_bhi + 2 * ks, kIdesc, 1u);
             }
             umma_commit(mma_done);
         }

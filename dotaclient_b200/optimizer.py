@@ -707,6 +707,10 @@ class DotaOptimizer:
             batch.old_logp, batch.advantages, batch.returns, self.e_clip, self.entropy_coef, self.vf_coef)
         self._n_actions[:5].copy_(n_actions)
         torch.autograd.backward([packed, logits['target_unit']], [d_packed, d_tu])                     # :672
+        # drop every reference into this step's autograd graph: a graph kept alive until the next forward keeps its saved
+        # activations (GBs) AND the parameters' AccumulateGrad nodes, whose stream then mismatches a later graph capture
+        self.policy_base._packed_heads = None
+        del logits, values, packed, d_packed, d_tu
         self.flat.gather_grads()
         # distributed.py:29-57 -> flags + ONE all-reduce; divide fused into the finish kernel
         ops.grad_flags(self.flat.grad_full, self.flat.total, self.flat.seg_head, self._n_actions)
