@@ -303,8 +303,8 @@ def run_stream(args, cfg):
                                                  "(>=1024 seqs x 16 per iteration, 4 epochs, hidden 256 GRU); 'step' = one train() call "
                                                  "including its share of experience prep", "agents": agents * world,
                                      "parallelism": "dp%d" % world}})
-    if world > 1:
-        dist.destroy_process_group()
+    opt.close()
+    finish_process(world)
 
 
 _REAL_STDOUT = None
@@ -403,6 +403,8 @@ def measure_config(cfg, args, world, rank, dev, steps, warmup, with_e2e):
     graphed = any(isinstance(v, tuple) for v in opt._graphs.values())
     # (2) the same steps launch by launch with CUDA events around every C-ABI call: the per-kernel table of the roofline
     ops.PROFILE.reset(enabled=True)
+    step_dev()                                  # untimed: the launch-by-launch path re-grows its allocator pool after the capture
+    ops.PROFILE.reset(enabled=True)
     ms_eager = timed(step_dev, steps)
     prof = ops.PROFILE.summary(steps)
     prof_bytes = {k: v / steps for k, v in ops.PROFILE.bytes.items()}
@@ -442,6 +444,7 @@ def measure_config(cfg, args, world, rank, dev, steps, warmup, with_e2e):
             out["ms_e2e_list_api"] = timed(lambda: opt.train(seqs_host), steps) / steps
         log("[%s] timed region (e2e): %.2f ms/step" % (cfg["name"], out["ms_e2e"]))
         del batch_host, seqs_host
+    opt.close()                                 # captured graphs (with NCCL work when data-parallel) go before the process group does
     del batch_dev, opt
     torch.cuda.empty_cache()
     return out
@@ -602,8 +605,7 @@ def main():
                 torch.cuda.empty_cache()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_process(world)
         return
     ms_per_step = meas["ms_per_step"]
     value = world * 1000.0 / ms_per_step
@@ -672,8 +674,25 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample,
                                 "sample_batch": b_sample, "scale_factor": b_sample / float(B)}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_process(world)
+
+
+def finish_process(world):
+    """Orderly end of a rank: everything on the device done, all ranks at the barrier, process group destroyed -- under a
+    watchdog, so that a teardown problem can never hold the driver's torchrun after the JSON line is out."""
+    import torch
+    import torch.distributed as dist
+    if world <= 1:
+        return
+    def bail():
+        os._exit(0)
+    t = threading.Timer(30.0, bail)
+    t.daemon = True
+    t.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    t.cancel()
 
 
 if __name__ == "__main__":

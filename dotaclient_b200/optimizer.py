@@ -415,6 +415,16 @@ class DotaOptimizer:
         self.mq.connect()
         self.upload_model(version=self.iteration_start)                  # :284
 
+    def close(self):
+        """Releases the captured step graphs (they hold NCCL work when data-parallel: destroy them BEFORE
+        ``dist.destroy_process_group()``, which otherwise waits forever) and the pinned staging buffers."""
+        self._graphs.clear()
+        self._staging.clear()
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def _sync_resume_state(self):
         """Data-parallel resume: only the master scans ``log_dir`` and restores (``checkpoint = is_master()``, :751), so the
         restored Adam moments, step counters and ``iteration_start`` are broadcast from rank 0 -- otherwise the replicas

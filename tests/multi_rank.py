@@ -49,6 +49,8 @@ def step_worker(rank, world, port, out_dir):
                      float(g["unclipped"]), float(g["clipped"])))
     torch.save({"recs": recs, "sd": {k: v.cpu() for k, v in opt.policy_base.state_dict().items()}},
                os.path.join(out_dir, "rank%d.pt" % rank))
+    opt.close()                                                         # graphs with NCCL work die before the process group
+    dist.barrier()
     dist.destroy_process_group()
 
 
@@ -69,6 +71,9 @@ def resume_worker(rank, world, port, out_dir):
     opt2.train(xs2)
     torch.save({"iteration_start": opt2.iteration_start, "steps": opt2.adam_steps.cpu(), "exp_avg": opt2.exp_avg.cpu(),
                 "param": opt2.flat.param.cpu(), "exp_avg_before": opt.exp_avg.cpu()}, os.path.join(out_dir, "resume%d.pt" % rank))
+    opt.close()
+    opt2.close()
+    dist.barrier()
     dist.destroy_process_group()
 
 
