@@ -42,11 +42,6 @@ constexpr int kProducerGroups = 3;
 constexpr int kMmaWarp = 4 * kProducerGroups;
 constexpr int kThreads = (kMmaWarp + 1 + 4) * 32;
 constexpr int kAccCols = 128, kTmemCols = 256;       // two accumulator buffers
-// MMA issue: one thread needs ~100 cycles of scalar work (64-bit descriptor arithmetic, R2UR moves) per tcgen05.mma, more than
-// the 64 cycles the M128 N128 K8 instruction occupies the tensor pipe (measured on the recurrence kernel, profiles/
-// r2_rnn_cluster_ncu.md); the four k-steps of a 32-wide chunk are therefore issued by FOUR lanes of the MMA warp in lockstep
-// (the scalar work is shared, SIMT), each lane committing its own MMAs to the stage / accumulator barriers.
-constexpr int kIssuers = BK / 8;
 constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -189,8 +184,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
     const int tiles_mn = m_blocks * n_blocks, tiles_total = tiles_mn * ksplit;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], kIssuers); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], kIssuers); mbar_init(&acc_empty[a], 4); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {   // TMEM allocation: one full warp; the address lands in shared memory
@@ -235,20 +230,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_kernel(const float *_
             for (int kc = 0; kc < k_chunks; ++kc) {
                 mbar_wait(&full[stage], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane < kIssuers) {                                          // lane = k-step (UMMA_K = 8 tf32 = 32 bytes = 2 x 16 B)
+                if (lane == 0) {
                     const uint32_t base = smem_u32(tiles + (size_t)stage * kStageBytes);
-                    const uint64_t adv = (uint64_t)(lane * 2);
-                    const uint64_t a_hi = make_desc(base) + adv, a_lo = make_desc(base + kTileBytes) + adv;
-                    const uint64_t b_hi = make_desc(base + 2 * kTileBytes) + adv, b_lo = make_desc(base + 3 * kTileBytes) + adv;
-                    if (kc == 0) {          // the tile's first MMA overwrites the accumulator: lane 0 issues it alone, the rest follow
-                        if (lane == 0) umma_tf32(tmem_d, a_lo, b_hi, kIdesc, 0u);
-                        __syncwarp((1u << kIssuers) - 1);
-                        if (lane != 0) umma_tf32(tmem_d, a_lo, b_hi, kIdesc, 1u);
-                    } else {
-                        umma_tf32(tmem_d, a_lo, b_hi, kIdesc, 1u);                   // small terms first
+                    const uint64_t a_hi = make_desc(base), a_lo = make_desc(base + kTileBytes);
+                    const uint64_t b_hi = make_desc(base + 2 * kTileBytes), b_lo = make_desc(base + 3 * kTileBytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {                      // UMMA_K = 8 tf32 = 32 bytes = 2 x 16 B
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t first = (kc | ks) != 0;
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, kIdesc, first);   // small terms first
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, kIdesc, 1u);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, kIdesc, 1u);
                     }
-                    umma_tf32(tmem_d, a_hi, b_lo, kIdesc, 1u);
-                    umma_tf32(tmem_d, a_hi, b_hi, kIdesc, 1u);
                     umma_commit(&empty[stage]);                                 // stage reusable once these MMAs retire
                     if (kc == k_chunks - 1) umma_commit(&acc_full[a]);          // accumulator complete
                 }
@@ -416,8 +409,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const fl
     const int n0 = n_blk * BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], kIssuers); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], kIssuers); mbar_init(&acc_empty[a], 4); }
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         mbar_init(w_ready, 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -494,20 +487,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const fl
                 const int stage = c % kWStages;
                 mbar_wait(&full[stage], (c / kWStages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (lane < kIssuers) {                                       // lane = k-step (see kIssuers)
+                if (lane == 0) {
                     const uint32_t xbase = smem_u32(tiles + (size_t)stage * kWStageBytes);
-                    const uint64_t adv = (uint64_t)(lane * 2);               // 32 bytes along K inside the 128-byte swizzle row
-                    const uint64_t x_hi = make_desc(xbase) + adv, x_lo = make_desc(xbase + kTileBytes) + adv;
-                    const uint32_t kcol = kc * BK + lane * 8;
-                    if (kc == 0) {          // the tile's first MMA overwrites the accumulator: lane 0 issues it alone, the rest follow
-                        if (lane == 0) umma_tf32_ts(tmem_d, tmem_w_lo + kcol, x_hi, kIdesc, 0u);
-                        __syncwarp((1u << kIssuers) - 1);
-                        if (lane != 0) umma_tf32_ts(tmem_d, tmem_w_lo + kcol, x_hi, kIdesc, 1u);
-                    } else {
-                        umma_tf32_ts(tmem_d, tmem_w_lo + kcol, x_hi, kIdesc, 1u);
+                    const uint64_t x_hi = make_desc(xbase), x_lo = make_desc(xbase + kTileBytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);             // 32 bytes along K inside the 128-byte swizzle row
+                        const uint32_t kcol = kc * BK + ks * 8;
+                        const uint32_t first = (kc | ks) != 0;
+                        umma_tf32_ts(tmem_d, tmem_w_lo + kcol, x_hi + adv, kIdesc, first);
+                        umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_lo + adv, kIdesc, 1u);
+                        umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_hi + adv, kIdesc, 1u);
                     }
-                    umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_lo, kIdesc, 1u);
-                    umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_hi, kIdesc, 1u);
                     umma_commit(&empty[stage]);
                     if (kc == k_chunks - 1) umma_commit(&acc_full[a]);
                 }
@@ -654,9 +645,9 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const fl
     const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], kIssuers); }
-        for (int s = 0; s < kGBStages; ++s) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], kIssuers); }
-        mbar_init(acc_full, kIssuers);
+        for (int s = 0; s < kGAStages; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kGBStages; ++s) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], 1); }
+        mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kGMmaWarp) {
@@ -766,20 +757,18 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const fl
             mbar_wait(&a_full[sa], (j / kGAStages) & 1);
             mbar_wait(&b_full[sb], (j / kGBStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane < kIssuers) {                                             // lane = k-step: 8 tokens = two 4-token groups per MMA
+            if (lane == 0) {
                 const uint32_t base = smem_u32(tiles + (size_t)sb * 2 * kTileBytes);
-                const uint32_t a_hi = tmem_a0 + sa * 64 + 8 * lane, a_lo = a_hi + 32;
-                const uint32_t adv = lane * 2 * kKGroupBytes;
-                const uint64_t b_hi = make_desc_mn(base + adv), b_lo = make_desc_mn(base + kTileBytes + adv);
-                if (j == 0) {               // the first MMA overwrites the accumulator: lane 0 issues it alone, the rest follow
-                    if (lane == 0) umma_tf32_ts(tmem_base, a_lo, b_hi, kIdescBMN, 0u);
-                    __syncwarp((1u << kIssuers) - 1);
-                    if (lane != 0) umma_tf32_ts(tmem_base, a_lo, b_hi, kIdescBMN, 1u);
-                } else {
-                    umma_tf32_ts(tmem_base, a_lo, b_hi, kIdescBMN, 1u);
+                const uint32_t a_hi0 = tmem_a0 + sa * 64, a_lo0 = a_hi0 + 32;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {                          // 8 tokens = two 4-token groups per MMA
+                    const uint32_t adv = ks * 2 * kKGroupBytes;
+                    const uint64_t b_hi = make_desc_mn(base + adv), b_lo = make_desc_mn(base + kTileBytes + adv);
+                    const uint32_t first = (j | ks) != 0;
+                    umma_tf32_ts(tmem_base, a_lo0 + 8 * ks, b_hi, kIdescBMN, first);
+                    umma_tf32_ts(tmem_base, a_hi0 + 8 * ks, b_lo, kIdescBMN, 1u);
+                    umma_tf32_ts(tmem_base, a_hi0 + 8 * ks, b_hi, kIdescBMN, 1u);
                 }
-                umma_tf32_ts(tmem_base, a_hi, b_lo, kIdescBMN, 1u);
-                umma_tf32_ts(tmem_base, a_hi, b_hi, kIdescBMN, 1u);
                 umma_commit(&a_empty[sa]);
                 umma_commit(&b_empty[sb]);
                 if (j == my_chunks - 1) umma_commit(acc_full);
