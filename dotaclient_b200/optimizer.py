@@ -569,21 +569,20 @@ class DotaOptimizer:
             self._staging_event.synchronize()          # the previous iteration's uploads have left the staging buffers
 
         def batched(group, key, dtype):
-            """Rollouts -> one time-major ``[Lmax, R, ...]`` tensor, stacked straight into a cached PINNED staging buffer
-            (multi-threaded host copy) and uploaded asynchronously."""
+            """Rollouts -> one time-major ``[Lmax, R, ...]`` device tensor.  The host side only does contiguous per-rollout
+            copies into a cached PINNED ``[R, Lmax, ...]`` staging buffer (memcpy speed; stacking time-major on the host is a
+            768-byte-granular scatter, 3x slower) and uploads asynchronously; the transposition to time-major runs on the GPU."""
             srcs = [torch.as_tensor(d[group][key]) for d in datas]
-            shape = (Lmax, R) + tuple(srcs[0].shape[1:])
+            shape = (R, Lmax) + tuple(srcs[0].shape[1:])
             buf = self._staging.get((group, key))
             if buf is None or buf.shape != shape or buf.dtype != dtype:
                 buf = torch.empty(shape, dtype=dtype).pin_memory()
                 self._staging[(group, key)] = buf
-            if same:                                                                   # no padding anywhere: one stack
-                torch.stack([t.to(dtype) for t in srcs], dim=1, out=buf)
-            else:
-                buf.zero_()                                                            # zero padding (:367-382)
-                for i, t in enumerate(srcs):
-                    buf[:Ls[i], i].copy_(t)
-            return buf.to(dev, non_blocking=True)
+            for i, t in enumerate(srcs):
+                buf[i, :Ls[i]].copy_(t)
+                if Ls[i] < Lmax:
+                    buf[i, Ls[i]:].zero_()                                             # zero padding (:367-382)
+            return buf.to(dev, non_blocking=True).transpose(0, 1).contiguous()
 
         obs = {k: batched('observations', k, torch.float32) for k in Policy.INPUT_KEYS}
         masks = {k: batched('masks', k, torch.bool) for k in Policy.OUTPUT_KEYS}
