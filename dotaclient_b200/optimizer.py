@@ -407,6 +407,7 @@ class DotaOptimizer:
         self._rollout_q, self._prefetch_thread = None, None
         self.use_cuda_graph = True          # replay device-resident batches of a known shape from a captured graph of the step
         self._graphs = {}
+        self._last_iteration_shape = None
         self.time_last_it = time.time()
 
         self.mq = mq if mq is not None else MessageQueue(host=self.rmq_host, port=self.rmq_port,
@@ -744,6 +745,8 @@ class DotaOptimizer:
             self._graphs[key] = "seen"
             return self._enqueue_step(batch)
         if entry == "seen":
+            for k in [k for k, v in self._graphs.items() if isinstance(v, tuple)][:-1]:
+                del self._graphs[k]            # at most two captured shapes alive: a graph pins its step's activations
             entry = self._capture_step(batch)
             self._graphs[key] = entry
             if entry == "eager":
@@ -822,6 +825,11 @@ class DotaOptimizer:
             experiences.extend(sequences)
         batch = ExperienceBatch.from_sequences(experiences, self.device)  # stacked once, reused by every epoch
         time_xp = time.time() - start_xp
+        # a stream of rollouts gives every iteration its own batch size: capturing a graph per shape would cost more than the
+        # `epochs` replays return, so the graph path is used only while consecutive iterations keep the same shape
+        shape = (batch.seq_len, batch.batch_size)
+        graph_setting, self.use_cuda_graph = self.use_cuda_graph, self.use_cuda_graph and shape == self._last_iteration_shape
+        self._last_iteration_shape = shape
 
         losses, entropies, grad_norms = [], [], []
         start_optimizing = time.time()
@@ -832,6 +840,7 @@ class DotaOptimizer:
             entropies.append(entropy_d)
             grad_norms.append(grad_norm_d)
         time_optimizing = time.time() - start_optimizing
+        self.use_cuda_graph = graph_setting
 
         losses = self.list_of_dicts_to_dict_of_lists(losses)
         entropies = self.list_of_dicts_to_dict_of_lists(entropies)
