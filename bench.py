@@ -202,7 +202,7 @@ def workload_config(cfg, n_gpus, where):
             "batch_per_gpu": cfg["batch"], "global_batch": cfg["batch"] * n_gpus, "seq_len": cfg["seq_len"],
             "hidden": cfg["hidden"], "cell": cfg["cell"], "parallelism": "dp%d" % n_gpus,
             "l2": "per-step inputs exceed the 126 MB L2" if cfg["batch"] * cfg["seq_len"] * 2100 > 126e6
-                  else "L2 flushed between steps", "where": where}
+                  else "working set below the 126 MB L2 (stated, not flushed: C1 is the reference's latency case)"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
