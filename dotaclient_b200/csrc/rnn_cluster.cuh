@@ -281,18 +281,17 @@ __global__ void __launch_bounds__(kThreads, 1) fwd_cluster_kernel(float *gates, 
         {
             const int q = warp & 3, cgp = warp >> 2;                               // TMEM lane quadrant (= gate), 8-column group
             const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 8 * cgp;
-            float sum[8];
-            uint32_t r[8];
-            tmem_ld8(taddr, r);
+            uint32_t r[8][8];                                                      // all eight loads in flight, one wait
+#pragma unroll
+            for (int p = 0; p < 8; ++p) tmem_ld8(taddr + 32 * p, r[p]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float sum[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sum[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 8; ++j) {
+                float a = __uint_as_float(r[0][j]);
 #pragma unroll
-            for (int p = 1; p < 8; ++p) {
-                tmem_ld8(taddr + 32 * p, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 8; ++j) sum[j] += __uint_as_float(r[j]);
+                for (int p = 1; p < 8; ++p) a += __uint_as_float(r[p][j]);         // fixed order: deterministic
+                sum[j] = a;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) scratch[(q * kNB + 8 * cgp + j) * 32 + lane] = sum[j];
@@ -538,18 +537,17 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_cluster_kernel(float *gates, 
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {   // partial dh_{t-1}[b][k] of this CTA's 128 gate columns -> scratch [buffer][cluster][rank][b][k]
             const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + 32 * (4 * mt) + 16 * wh;
-            float sum[16];
-            uint32_t r[16];
-            tmem_ld16(taddr, r);
+            uint32_t r[G][16];                                                     // all G loads in flight, one wait
+#pragma unroll
+            for (int p = 0; p < G; ++p) tmem_ld16(taddr + 32 * p, r[p]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float sum[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 16; ++j) {
+                float a = __uint_as_float(r[0][j]);
 #pragma unroll
-            for (int p = 1; p < G; ++p) {
-                tmem_ld16(taddr + 32 * p, r);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sum[j] += __uint_as_float(r[j]);
+                for (int p = 1; p < G; ++p) a += __uint_as_float(r[p][j]);
+                sum[j] = a;
             }
             float *dst = part + (((size_t)((it & 1) * ncl + cl) * kCL + rank) * kNB + 16 * wh) * H + mt * 128 + q * 32 + lane;
 #pragma unroll
