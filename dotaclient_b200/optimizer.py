@@ -327,6 +327,7 @@ def all_gather(t):                                                        # :193
 class DotaOptimizer:
     MODEL_FILENAME_FMT = "model_%09d.pt"
     ADAM_FILENAME_FMT = "adam_%09d.state"         # extension: Adam moments of the same iteration (torch.optim.Adam layout)
+    ADAM_FILES_KEPT = 3
     BUCKET_NAME = 'dotaservice'
     MODEL_HISTOGRAM_FREQ = 128
     MAX_GRAD_NORM = 0.5
@@ -466,6 +467,9 @@ class DotaOptimizer:
             # extension: the Adam moments next to the weights, in torch.optim.Adam's own format.  The name
             # does not end in .pt, so the reference's "latest *.pt" scan and its agents never see it.
             torch.save(self.optimizer.state_dict(), os.path.join(self.log_dir, self.ADAM_FILENAME_FMT % version))
+            stale = sorted(f for f in os.listdir(self.log_dir) if re.fullmatch(r'adam_\d{9}\.state', f))[:-self.ADAM_FILES_KEPT]
+            for f in stale:                                                 # resume only ever needs the newest: bound the disk growth
+                os.remove(os.path.join(self.log_dir, f))
         self.mq.publish_model(msg=state_dict_b, hdr={'version': version})   # :716
 
     # -- experience intake (:314-430) -------------------------------------------------------------
@@ -947,6 +951,10 @@ def main(rmq_host, rmq_port, epochs, min_seq_per_epoch, seq_len, learning_rate,
         learning_rate=learning_rate, checkpoint=is_master(), pretrained_model=pretrained_model,
         mq_prefetch_count=mq_prefetch_count, log_dir=log_dir, entropy_coef=entropy_coef, vf_coef=vf_coef,
         run_local=run_local, hidden_size=hidden_size, cell=cell)
+    if isinstance(dota_optimizer.mq, MessageQueue):
+        logger.warning('the built-in MessageQueue is an IN-PROCESS broker (the AMQP transport is out of scope): with no producer '
+                       'thread publishing to it in this process run() will wait forever; pass mq=<your pika-backed queue> to '
+                       'DotaOptimizer for a RabbitMQ deployment (--ip/--port are accepted for CLI compatibility only)')
     dota_optimizer.run()
 
 
