@@ -475,13 +475,18 @@ class DotaOptimizer:
     # -- experience intake (:314-430) -------------------------------------------------------------
     def get_rollout(self):
         method, properties, body = self.mq.consume_xp()
-        data = pickle.loads(body)
+        return self._describe_rollout(pickle.loads(body))
+
+    @staticmethod
+    def _describe_rollout(data):
         rollout_len = data['rewards'].shape[0]
         subrewards = data['rewards'].sum(axis=0)
         return data, subrewards, rollout_len, data['weight_version'], data.get('canvas')
 
     def _next_rollout(self):
-        """``get_rollout()``, optionally served by the decode-ahead thread."""
+        """``get_rollout()``, optionally served by the decode-ahead thread -- same rollouts, same order as the reference's
+        one-at-a-time loop (:448-466).  (A pool of decoder PROCESSES was measured and dropped: ``pickle.loads`` of a 2.7 MB
+        rollout is 4 ms here, shipping the bytes out and the tensors back through shared memory costs 9x that.)"""
         if self.rollout_prefetch <= 0:
             return self.get_rollout()
         if self._prefetch_thread is None:
@@ -652,18 +657,32 @@ class DotaOptimizer:
 
     def batch_from_rollouts(self, datas):
         """Rollouts -> one stacked, time-major ``ExperienceBatch`` (what ``train`` consumes; :587-615 stacks the same
-        sequences batch-first).  When every rollout is exactly one ``seq_len`` chunk the prepared tensors ARE the batch (no
-        per-sequence slicing or re-stacking); otherwise the chunks go through ``ExperienceBatch.from_sequences``."""
-        S = self.seq_len
-        if all(int(d['rewards'].shape[0]) == S for d in datas):
-            p = self._prepare_rollouts(datas)
-            R = len(datas)
-            h0 = torch.zeros((1, R, self.policy_base.hidden_size), dtype=torch.float32, device=self.device)
-            c0 = torch.zeros_like(h0) if self.policy_base.cell == "lstm" else None
-            return ExperienceBatch(p['obs'], p['masks'], p['actions'], p['old_logp'], p['adv_c'].view(R, S).t().contiguous(),
-                                   p['ret_c'].view(R, S).t().contiguous(), h0, c0)
-        seqs = [s for group in self.experiences_from_rollouts(datas) for s in group]
-        return ExperienceBatch.from_sequences(seqs, self.device)
+        sequences batch-first), in the order ``experiences_from_rollouts`` emits them (rollout by rollout, chunk by chunk).
+        Built from the prepared ``[L_max, R, ...]`` tensors with a handful of tensor ops per ROLLOUT -- no per-sequence
+        Python objects, no per-sequence re-stacking (an iteration of the stream has ~1000 sequences of 16 steps)."""
+        S, pol = self.seq_len, self.policy_base
+        p = self._prepare_rollouts(datas)
+        R, Lps = len(datas), p['Lps']
+        n_chunks = [lp // S for lp in Lps]
+
+        def chunked(t):                       # [Lmax, R, ...] -> [S, sum(n_chunks), ...]
+            if p['same'] and p['Lmax'] == S:
+                return t
+            parts = [t[:Lps[i], i].reshape((n_chunks[i], S) + tuple(t.shape[2:])).transpose(0, 1) for i in range(R)]
+            return torch.cat(parts, dim=1)
+        obs = {k: chunked(v) for k, v in p['obs'].items()}
+        masks = {k: chunked(v) for k, v in p['masks'].items()}
+        actions = {k: chunked(v) for k, v in p['actions'].items()}
+        old_logp = chunked(p['old_logp'])
+        B = sum(n_chunks)
+        adv = p['adv_c'].view(B, S).t().contiguous()                  # the GAE outputs are rollout-major back-to-back segments
+        ret = p['ret_c'].view(B, S).t().contiguous()
+        # hidden state entering chunk j of rollout i = state buffer slot j*S (:340,384-385: carried, not re-zeroed)
+        t_idx = torch.tensor([j * S for i in range(R) for j in range(n_chunks[i])], dtype=torch.int64, device=self.device)
+        r_idx = torch.tensor([i for i in range(R) for _ in range(n_chunks[i])], dtype=torch.int64, device=self.device)
+        h0 = p['ybuf'][t_idx, r_idx].unsqueeze(0)
+        c0 = p['cbuf'][t_idx, r_idx].unsqueeze(0) if pol.cell == "lstm" else None
+        return ExperienceBatch(obs, masks, actions, old_logp, adv, ret, h0, c0)
 
     @staticmethod
     def list_of_dicts_to_dict_of_lists(x):
@@ -825,9 +844,7 @@ class DotaOptimizer:
             subrewards.append(rollout_subrewards)
             rollout_lens.append(rollout_len)
             weight_ages.append(it - weight_version)
-        for sequences in self.experiences_from_rollouts(rollouts):
-            experiences.extend(sequences)
-        batch = ExperienceBatch.from_sequences(experiences, self.device)  # stacked once, reused by every epoch
+        batch = self.batch_from_rollouts(rollouts)                        # prepared + stacked once, reused by every epoch
         time_xp = time.time() - start_xp
         # a stream of rollouts gives every iteration its own batch size: capturing a graph per shape would cost more than the
         # `epochs` replays return, so the graph path is used only while consecutive iterations keep the same shape
@@ -849,7 +866,7 @@ class DotaOptimizer:
         losses = self.list_of_dicts_to_dict_of_lists(losses)
         entropies = self.list_of_dicts_to_dict_of_lists(entropies)
         grad_norms = self.list_of_dicts_to_dict_of_lists(grad_norms)
-        n_steps = len(experiences) * self.seq_len                          # :486
+        n_steps = batch.batch_size * self.seq_len                          # :486 (len(experiences) * seq_len)
         subrewards_per_sec = np.stack(subrewards) / n_steps * Policy.OBSERVATIONS_PER_SECOND
         reward_dict = dict(zip(REWARD_KEYS, subrewards_per_sec.sum(axis=0)))
         time_it = time.time() - self.time_last_it

@@ -402,9 +402,16 @@ def test_batch_from_rollouts_equals_stacked_sequences(tmp_path):
             assert torch.equal(a, b), ka
         else:
             torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=ka)
-    ragged = [make_rollout(L, 80 + i) for i, L in enumerate((S, 2 * S + 3, S - 5))]
+    ragged = [make_rollout(L, 80 + i) for i, L in enumerate((S, 2 * S + 3, S - 5, 4 * S))]
     general = mine.batch_from_rollouts(copy.deepcopy(ragged))
-    assert general.batch_size == 1 + 3 + 1 and general.seq_len == S
+    assert general.batch_size == 1 + 3 + 1 + 4 and general.seq_len == S
+    slow2 = ExperienceBatch.from_sequences([s for grp in mine.experiences_from_rollouts(copy.deepcopy(ragged)) for s in grp], dev())
+    for (_, ka, a), (_, kb, b) in zip(general.tensors(), slow2.tensors()):
+        assert ka == kb and a.shape == b.shape, (ka, a.shape, b.shape)
+        if a.dtype == torch.bool:
+            assert torch.equal(a, b), ka
+        else:
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7, msg=ka)       # same kernels on the same data: (near-)identical
 
 
 @pytest.mark.parametrize("H,cell", [(256, "gru"), (128, "lstm")])
