@@ -388,6 +388,30 @@ def test_optimizer_step_long_bptt_vs_oracle(H, cell, S, B, tmp_path):
         assert cos > 0.9999, (names[i], float(cos))
 
 
+def test_graph_replay_equals_launch_by_launch(tmp_path):
+    """train() replayed from the CUDA graph of the step == the same step launched kernel by kernel: same losses, same
+    gradient norms, same parameters and Adam state after five steps (the graph is captured on the second call of a shape;
+    both optimizers start from the same seeded init and see the same batch)."""
+    S, B = 16, 6
+    a = make_optimizer(256, "gru", S, tmp_path)
+    b = make_optimizer(256, "gru", S, tmp_path)
+    b.use_cuda_graph = False
+    rollouts = [make_rollout(S, 40 + i) for i in range(B)]
+    batch_a = a.batch_from_rollouts(copy.deepcopy(rollouts))
+    batch_b = b.batch_from_rollouts(copy.deepcopy(rollouts))
+    for step in range(5):
+        la, ea, ga = a.train(batch_a)
+        lb, eb, gb = b.train(batch_b)
+        for k in la:
+            np.testing.assert_allclose(float(la[k]), float(lb[k]), rtol=1e-6, atol=1e-9, err_msg="%s step %d" % (k, step))
+        np.testing.assert_allclose(float(ga["unclipped"]), float(gb["unclipped"]), rtol=1e-6)
+    assert any(isinstance(v, tuple) for v in a._graphs.values()), "the step was never captured"
+    assert not any(isinstance(v, tuple) for v in b._graphs.values())
+    torch.testing.assert_close(a.flat.param, b.flat.param, rtol=1e-6, atol=1e-9)
+    torch.testing.assert_close(a.exp_avg, b.exp_avg, rtol=1e-5, atol=1e-12)
+    assert torch.equal(a.adam_steps, b.adam_steps)
+
+
 def test_batch_from_rollouts_equals_stacked_sequences(tmp_path):
     """The one-chunk fast path of batch_from_rollouts == ExperienceBatch.from_sequences over experiences_from_rollout."""
     from dotaclient_b200.optimizer import ExperienceBatch
