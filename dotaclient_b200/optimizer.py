@@ -408,6 +408,7 @@ class DotaOptimizer:
         self._rollout_q, self._prefetch_thread = None, None
         self.use_cuda_graph = True          # replay device-resident batches of a known shape from a captured graph of the step
         self._graphs = {}
+        self._input_slots = {}              # batch shape -> up to two sets of static device input buffers (prefetch + graph)
         self._last_iteration_shape = None
         self.time_last_it = time.time()
 
@@ -421,6 +422,7 @@ class DotaOptimizer:
         """Releases the captured step graphs (they hold NCCL work when data-parallel: destroy them BEFORE
         ``dist.destroy_process_group()``, which otherwise waits forever) and the pinned staging buffers."""
         self._graphs.clear()
+        self._input_slots.clear()
         self._staging.clear()
         import gc
         gc.collect()
@@ -702,7 +704,13 @@ class DotaOptimizer:
         else:
             batch = ExperienceBatch.from_sequences(experiences, self.device)
         t_enter = time.perf_counter()
-        if self.use_cuda_graph and not ops.H2D_EVENTS and not ops.PROFILE.enabled:
+        slot = getattr(batch, "_slot", None)
+        if slot is not None:                       # uploaded by prefetch() straight into a graph's static input buffers
+            torch.cuda.current_stream().wait_event(slot["ready"])
+            out, metrics = self._replay_step(batch, static=batch) if not ops.PROFILE.enabled else self._enqueue_step(batch)
+            slot["done"].record()
+            slot["busy"] = False
+        elif self.use_cuda_graph and not ops.H2D_EVENTS and not ops.PROFILE.enabled:
             out, metrics = self._replay_step(batch)
         else:
             out, metrics = self._enqueue_step(batch)
@@ -757,12 +765,13 @@ class DotaOptimizer:
         return out, self._metrics
 
     # -- CUDA graph of the step ----------------------------------------------------------------------
-    def _replay_step(self, batch):
+    def _replay_step(self, batch, static=None):
         """Replays the captured step for this batch shape (captures it the second time the shape is seen: the first call of
         a shape runs launch by launch, which also warms every kernel up).  Inputs are copied into the graph's static
-        buffers (device to device); parameters, gradients, Adam state and step counters are the same device buffers the
+        buffers (device to device) -- or, for a batch that ``prefetch`` uploaded into an input slot (``static`` = the batch
+        itself), are already there; parameters, gradients, Adam state and step counters are the same device buffers the
         eager path uses, so eager and graphed steps can be mixed freely."""
-        key = (batch.seq_len, batch.batch_size)
+        key = (batch.seq_len, batch.batch_size) if static is None else (batch.seq_len, batch.batch_size, id(static._slot))
         entry = self._graphs.get(key)
         if entry is None:
             self._graphs[key] = "seen"
@@ -770,27 +779,29 @@ class DotaOptimizer:
         if entry == "seen":
             for k in [k for k, v in self._graphs.items() if isinstance(v, tuple)][:-1]:
                 del self._graphs[k]            # at most two captured shapes alive: a graph pins its step's activations
-            entry = self._capture_step(batch)
+            entry = self._capture_step(batch, static)
             self._graphs[key] = entry
             if entry == "eager":
                 return self._enqueue_step(batch)
         elif entry == "eager":
             return self._enqueue_step(batch)
-        static, graph, out = entry
-        srcs = [v for _, _, v in batch.tensors()]
-        dsts = [v for _, _, v in static.tensors()]
-        torch._foreach_copy_(dsts, srcs)
+        graph_static, graph, out = entry
+        if static is None:
+            srcs = [v for _, _, v in batch.tensors()]
+            dsts = [v for _, _, v in graph_static.tensors()]
+            torch._foreach_copy_(dsts, srcs)
         graph.replay()
         return out, self._metrics
 
-    def _capture_step(self, batch):
-        static = ExperienceBatch({}, {}, {}, None, None, None, None, None)
-        for holder, k, v in batch.tensors():
-            c = v.detach().clone()
-            if isinstance(holder, dict):
-                (static.observations if holder is batch.observations else static.masks if holder is batch.masks else static.actions)[k] = c
-            else:
-                setattr(static, k, c)
+    def _capture_step(self, batch, static=None):
+        if static is None:
+            static = ExperienceBatch({}, {}, {}, None, None, None, None, None)
+            for holder, k, v in batch.tensors():
+                c = v.detach().clone()
+                if isinstance(holder, dict):
+                    (static.observations if holder is batch.observations else static.masks if holder is batch.masks else static.actions)[k] = c
+                else:
+                    setattr(static, k, c)
         graph = torch.cuda.CUDAGraph()
         try:
             torch.cuda.synchronize()
@@ -812,7 +823,44 @@ class DotaOptimizer:
             experiences = ExperienceBatch.from_sequences(experiences, torch.device("cpu")).pin_memory()
         if experiences.advantages.is_cuda:
             return experiences
+        if self.use_cuda_graph and experiences.advantages.is_pinned():
+            staged = self._stage_into_slot(experiences)
+            if staged is not None:
+                return staged
         return experiences.to(self.device, prefetch=True)
+
+    def _stage_into_slot(self, host):
+        """Double-buffered graph inputs: every batch shape owns TWO sets of static device input buffers; ``prefetch`` copies
+        the pinned host batch into the set that is not being trained on (copy stream, behind the replay that last read that
+        set) and ``train`` replays the graph captured over that set -- so the upload of step k+1 overlaps the graph of step k.
+        Returns None (caller falls back to per-tensor uploads) when both sets are still waiting to be trained on."""
+        key = (host.seq_len, host.batch_size)
+        slots = self._input_slots.setdefault(key, [])
+        slot = next((sl for sl in slots if not sl["busy"]), None)
+        if slot is None:
+            if len(slots) >= 2:
+                return None
+            dev_batch = ExperienceBatch({}, {}, {}, None, None, None, None, None)
+            for holder, k, v in host.tensors():
+                c = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                if isinstance(holder, dict):
+                    (dev_batch.observations if holder is host.observations else dev_batch.masks if holder is host.masks else dev_batch.actions)[k] = c
+                else:
+                    setattr(dev_batch, k, c)
+            slot = {"batch": dev_batch, "busy": False, "ready": torch.cuda.Event(), "done": torch.cuda.Event()}
+            slot["done"].record()
+            dev_batch._slot = slot
+            slots.append(slot)
+        side = _copy_stream(self.device)
+        side.wait_event(slot["done"])                    # the replay that last read these buffers has finished
+        with torch.cuda.stream(side):
+            dsts = [v for _, _, v in slot["batch"].tensors()]
+            srcs = [v for _, _, v in host.tensors()]
+            for d, src in zip(dsts, srcs):
+                d.copy_(src, non_blocking=True)
+            slot["ready"].record(side)
+        slot["busy"] = True
+        return slot["batch"]
 
     def mean_gradient_norm(self):
         """Mean per-tensor L2 norm over parameters that got a gradient in the last step (:691-695)."""

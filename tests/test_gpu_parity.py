@@ -412,6 +412,29 @@ def test_graph_replay_equals_launch_by_launch(tmp_path):
     assert torch.equal(a.adam_steps, b.adam_steps)
 
 
+def test_prefetch_into_graph_slots_equals_plain_train(tmp_path):
+    """The end-to-end path of the bench: pinned host batches uploaded by prefetch() into the two sets of static graph inputs,
+    one upload ahead of the step being trained -- same results as training the same batches from device memory."""
+    S, B = 16, 5
+    a = make_optimizer(128, "lstm", S, tmp_path)
+    b = make_optimizer(128, "lstm", S, tmp_path)
+    b.use_cuda_graph = False
+    batches = [a.batch_from_rollouts([make_rollout(S, 300 + 10 * j + i) for i in range(B)]) for j in range(3)]
+    hosts = [bt.pin_memory() for bt in batches]
+    order = [0, 1, 2, 0, 1, 2, 2, 0]
+    staged = a.prefetch(hosts[order[0]])
+    for n, j in enumerate(order):
+        nxt = a.prefetch(hosts[order[n + 1]]) if n + 1 < len(order) else None       # one upload ahead
+        la, _, ga = a.train(staged)
+        lb, _, gb = b.train(batches[j])
+        for k in la:
+            np.testing.assert_allclose(float(la[k]), float(lb[k]), rtol=1e-6, atol=1e-9, err_msg="%s step %d" % (k, n))
+        np.testing.assert_allclose(float(ga["unclipped"]), float(gb["unclipped"]), rtol=1e-6)
+        staged = nxt
+    assert sum(isinstance(v, tuple) for v in a._graphs.values()) == 2, "both input slots should be captured"
+    torch.testing.assert_close(a.flat.param, b.flat.param, rtol=1e-6, atol=1e-9)
+
+
 def test_batch_from_rollouts_equals_stacked_sequences(tmp_path):
     """The one-chunk fast path of batch_from_rollouts == ExperienceBatch.from_sequences over experiences_from_rollout."""
     from dotaclient_b200.optimizer import ExperienceBatch
