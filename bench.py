@@ -613,7 +613,7 @@ def main():
     # Per-kernel table (CUDA events on the launching stream, averaged per step) with each kernel's ALGORITHMIC HBM bytes
     # (inputs read once + outputs written once) -> achieved GB/s and fraction of the measured HBM peak.
     table = kernel_table(meas, peak)
-    families = {"tcgen05 3xTF32 GEMM, forward + data gradient (dc_gemm_tf32x3*)": ["gemm_tf32x3"],
+    families = {"tcgen05 3xTF32 GEMM, forward + data gradient (dc_gemm_tf32x3*, dc_gemm_unit_max)": ["gemm_tf32x3", "gemm_unit_max"],
                 "tcgen05 3xTF32 weight-gradient GEMM (dc_gemm_wgrad_tf32x3*)": ["gemm_wgrad"],
                 "recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)": ["rnn_fwd", "rnn_bwd"]}
     fam = {}

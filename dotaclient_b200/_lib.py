@@ -39,6 +39,9 @@ SIGNATURES = {
     "dc_unit_max_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
     "dc_unit_max_bwd": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     "dc_unit_grad_assemble": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "dc_gemm_unit_max": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
+    "dc_target_unit_q_fwd": (_i32, [_vp, _i32, _c.c_void_p * 6, _vp, _i64, _vp]),
+    "dc_target_unit_q_bwd": (_i32, [_vp, _c.c_void_p * 6, _vp, _i32, _i64, _vp]),
     "dc_target_unit_fwd": (_i32, [_vp, _vp, _vp, _i64, _vp]),
     "dc_target_unit_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "dc_ppo_loss_fwd_bwd": (_i32, [_ptr5, _ptr5, _ptr5, _vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _ptr5, _vp, _vp,

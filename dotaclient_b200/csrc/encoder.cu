@@ -520,6 +520,80 @@ __global__ void __launch_bounds__(kThreadsE) unit_grad_assemble_kernel(const flo
 
 int grid_rows(int64_t rows_per_block_iter_unused) { (void)rows_per_block_iter_unused; return 4 * dc_sm_count(); }
 
+
+// ---- target-unit head without the unit embedding ------------------------------------------------------------------------
+// logits[n,u] = <att[n], W_g basic[n,u] + b_g> = <att[n] W_g, basic[n,u]> + <att[n], b_g> (policy.py:144-153; algebra pinned in
+// tests/test_oracle.py): with q[n, g*128 + j] = (att W_g)[n, j] and q[n, 768 + g] = <att[n], b_g> from ONE small GEMM over tokens,
+// the head reads the stored `basic` rows and the [N, 40, 128] embedding is never materialised.
+struct BasicPtrs { const float *p[6]; };
+__constant__ int kGroupUnits[6] = {1, 5, 16, 16, 1, 1};
+__constant__ int kGroupOffset[6] = {0, 1, 6, 22, 38, 39};
+
+__global__ void __launch_bounds__(kThreadsE) target_unit_q_fwd_kernel(const float *__restrict__ q, int ld_q, BasicPtrs basics,
+                                                                      float *__restrict__ logits, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float *qrow = q + n * ld_q;
+    float mine = 0.f, mine_hi = 0.f;                              // lane u keeps logit u (u < 32), lanes 0..7 also u+32
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(qrow + g * kC) + lane);
+        const float c = __ldg(qrow + 6 * kC + g);
+        const int nu = kGroupUnits[g], off = kGroupOffset[g];
+        const float4 *row = reinterpret_cast<const float4 *>(basics.p[g] + n * nu * kC) + lane;
+        for (int u = 0; u < nu; ++u) {
+            const float4 v = __ldg(row + u * (kC / 4));
+            float d = v.x * a.x + v.y * a.y + v.z * a.z + v.w * a.w;
+            d = dc_warp_sum(d) + c;
+            const int o = off + u;
+            if (o < 32) { if (lane == o) mine = d; } else { if (lane == o - 32) mine_hi = d; }
+        }
+    }
+    logits[n * kMaxUnits + lane] = mine;
+    if (lane < kMaxUnits - 32) logits[n * kMaxUnits + 32 + lane] = mine_hi;
+}
+
+// s[n, g*128 + j] = sum_u dlogits[n, off_g + u] basic_g[n,u,j],  s[n, 768 + g] = sum_u dlogits[n, off_g + u]  (zeros elsewhere):
+// d_att = s [W_0 | ... | W_5 | b_0..b_5]^T is then one GEMM over tokens.  Tokens that did not use the head write zeros, read nothing.
+__global__ void __launch_bounds__(kThreadsE) target_unit_q_bwd_kernel(const float *__restrict__ dlogits, BasicPtrs basics,
+                                                                      float *__restrict__ s, int ld_s, int64_t N) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float g_lo = dlogits[n * kMaxUnits + lane];
+    const float g_hi = lane < kMaxUnits - 32 ? dlogits[n * kMaxUnits + 32 + lane] : 0.f;
+    const bool any = __any_sync(0xffffffffu, g_lo != 0.f || g_hi != 0.f);
+    float4 *srow = reinterpret_cast<float4 *>(s + n * ld_s) + lane;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!any) {
+#pragma unroll
+        for (int g = 0; g < 7; ++g) srow[g * (kC / 4)] = zero;
+        return;
+    }
+    float sig[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) {
+        const int nu = kGroupUnits[g], off = kGroupOffset[g];
+        const float4 *row = reinterpret_cast<const float4 *>(basics.p[g] + n * nu * kC) + lane;
+        float4 acc = zero;
+        float sg = 0.f;
+        for (int u = 0; u < nu; ++u) {
+            const int o = off + u;
+            const float gv = __shfl_sync(0xffffffffu, o < 32 ? g_lo : g_hi, o & 31);
+            const float4 v = __ldg(row + u * (kC / 4));
+            acc.x = fmaf(gv, v.x, acc.x); acc.y = fmaf(gv, v.y, acc.y); acc.z = fmaf(gv, v.z, acc.z); acc.w = fmaf(gv, v.w, acc.w);
+            sg += gv;
+        }
+        srow[g * (kC / 4)] = acc;
+        sig[g] = sg;
+    }
+    float4 tail = zero;                                            // columns 768..895: the six sums, then zeros
+    if (lane == 0) tail = make_float4(sig[0], sig[1], sig[2], sig[3]);
+    if (lane == 1) tail = make_float4(sig[4], sig[5], 0.f, 0.f);
+    srow[6 * (kC / 4)] = tail;
+}
+
 }  // namespace
 
 extern "C" int dc_unit_basic_fwd(const float *units, const float *w_b, const float *b_b, float *basic, int64_t R,
@@ -608,6 +682,34 @@ extern "C" int dc_target_unit_fwd(const float *att, const float *ue, float *logi
     DC_REQUIRE(att && ue && logits && N > 0, DC_EINVAL, "dc_target_unit_fwd: bad arguments");
     DC_REQUIRE((((uintptr_t)att | (uintptr_t)ue) & 15) == 0, DC_EINVAL, "dc_target_unit_fwd: alignment");
     target_unit_fwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(att, ue, logits, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_target_unit_q_fwd(const float *q, int ld_q, const float *const basics[6], float *logits, int64_t N,
+                                    dc_stream_t stream) {
+    DC_REQUIRE(q && basics && logits && N > 0 && ld_q >= 7 * kC && ld_q % 4 == 0, DC_EINVAL, "dc_target_unit_q_fwd: bad arguments");
+    BasicPtrs bp;
+    for (int g = 0; g < 6; ++g) {
+        DC_REQUIRE(basics[g] && ((uintptr_t)basics[g] & 15) == 0, DC_EINVAL, "dc_target_unit_q_fwd: basic[%d] null / unaligned", g);
+        bp.p[g] = basics[g];
+    }
+    DC_REQUIRE(((uintptr_t)q & 15) == 0, DC_EINVAL, "dc_target_unit_q_fwd: alignment");
+    target_unit_q_fwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(q, ld_q, bp, logits, N);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
+extern "C" int dc_target_unit_q_bwd(const float *dlogits, const float *const basics[6], float *s, int ld_s, int64_t N,
+                                    dc_stream_t stream) {
+    DC_REQUIRE(dlogits && basics && s && N > 0 && ld_s >= 7 * kC && ld_s % 4 == 0, DC_EINVAL, "dc_target_unit_q_bwd: bad arguments");
+    BasicPtrs bp;
+    for (int g = 0; g < 6; ++g) {
+        DC_REQUIRE(basics[g] && ((uintptr_t)basics[g] & 15) == 0, DC_EINVAL, "dc_target_unit_q_bwd: basic[%d] null / unaligned", g);
+        bp.p[g] = basics[g];
+    }
+    DC_REQUIRE(((uintptr_t)s & 15) == 0, DC_EINVAL, "dc_target_unit_q_bwd: alignment");
+    target_unit_q_bwd_kernel<<<(unsigned)((N + kWarps - 1) / kWarps), kThreadsE, 0, dc_cu_stream(stream)>>>(dlogits, bp, s, ld_s, N);
     DC_LAUNCH_OK();
     return DC_OK;
 }

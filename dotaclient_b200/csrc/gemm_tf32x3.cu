@@ -392,10 +392,17 @@ __device__ __forceinline__ void store_feature32(float *__restrict__ C, RowMap cm
     else if (n > 0) store_feature32_impl<false>(C, cmap, tok0, n, col, r, bias, relu, lane);
 }
 
+// NU > 0: "unit max" epilogue for the unit-embedding layers (policy.py:101-127): the rows are (token, unit) pairs, NU units
+// per token; instead of storing the [M, 128] embedding the epilogue reduces every token's NU rows to their maximum (+ bias)
+// and the index of the maximising unit: C[token * cmap.ld + feature] (and C_copy, policy.py:127), argmax[token * 128 + feature].
+// Tiles advance by kTileRows = 128 - 128 % NU rows (125 for the 5-unit group) so that a token never straddles two tiles.
+template <int NU>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const float *__restrict__ A, RowMap amap,
                                                                         const float *__restrict__ B, int ldb,
                                                                         const float *__restrict__ bias, float *__restrict__ C,
-                                                                        RowMap cmap, int M, int N, int K, int relu) {
+                                                                        RowMap cmap, int M, int N, int K, int relu,
+                                                                        float *__restrict__ C_copy, uint8_t *__restrict__ argmax) {
+    constexpr int kTileRows = NU > 0 ? BM - BM % NU : BM;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kWStages * kWStageBytes);
@@ -404,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const fl
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kWStages + 5);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_blocks = (M + BM - 1) / BM, n_blocks = N / BN, k_chunks = K / BK;
+    const int m_blocks = (M + kTileRows - 1) / kTileRows, n_blocks = N / BN, k_chunks = K / BK;
     const int n_blk = blockIdx.x % n_blocks, m_first = blockIdx.x / n_blocks, m_step = gridDim.x / n_blocks;
     const int n0 = n_blk * BN;
 
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const fl
         const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
         float4 va[8], vb[8];
         auto fetch = [&](uint32_t cc, float4 (&buf)[8]) {
-            if (cc < total_chunks) tile_load_k(A, amap, (m_first + (int)(cc / k_chunks) * m_step) * BM, M, (int)(cc % k_chunks) * BK, t, buf);
+            if (cc < total_chunks) tile_load_k(A, amap, (m_first + (int)(cc / k_chunks) * m_step) * kTileRows, M, (int)(cc % k_chunks) * BK, t, buf);
         };
         auto emit = [&](uint32_t cc, const float4 (&buf)[8]) {
             const int stage = cc % kWStages;
@@ -514,26 +521,89 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const fl
         int it = 0;
         for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
             const int a = it & 1;
-            const int m0 = mb * BM;
+            const int m0 = mb * kTileRows;
             mbar_wait(&acc_full[a], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(a * kAccCols);
-            uint32_t ra[32], rb[32];
-            tmem_ld32(taddr, ra);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tmem_ld32(taddr + 32, rb);
-            store_feature32(C, cmap, m0, M, col, ra, bias_f, relu, lane);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tmem_ld32(taddr + 64, ra);
-            store_feature32(C, cmap, m0 + 32, M, col, rb, bias_f, relu, lane);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            tmem_ld32(taddr + 96, rb);
-            store_feature32(C, cmap, m0 + 64, M, col, ra, bias_f, relu, lane);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // accumulator fully read: hand it back early
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
-            store_feature32(C, cmap, m0 + 96, M, col, rb, bias_f, relu, lane);
+            if constexpr (NU > 0) {
+                // thread = output feature; the accumulator columns are the tile's rows = (token, unit) pairs in order
+                const int tok0 = m0 / NU, n_tok = M / NU;
+                float best = 0.f;
+                int best_u = 0;
+#pragma unroll
+                for (int ld = 0; ld < 4; ++ld) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + 32 * ld, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ld == 3) {                                                  // accumulator fully read: hand it back early
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[a]);
+                    }
+                    if constexpr (NU == 16) {
+                        // two whole tokens per load: maximum by a 4-level tree, arg-max = first unit that equals it (torch.max) --
+                        // independent instructions instead of a 16-long dependent compare/select chain
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float v[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) v[u] = __uint_as_float(r[16 * h + u]);
+                            float m8[8], m4[4];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) m8[u] = fmaxf(v[2 * u], v[2 * u + 1]);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) m4[u] = fmaxf(m8[2 * u], m8[2 * u + 1]);
+                            const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                            int i8[8], i4[4];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) i8[u] = v[2 * u] == m ? 2 * u : (v[2 * u + 1] == m ? 2 * u + 1 : 16);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) i4[u] = min(i8[2 * u], i8[2 * u + 1]);
+                            const int am = min(min(i4[0], i4[1]), min(i4[2], i4[3]));
+                            const int tok = tok0 + 2 * ld + h;
+                            if (tok < n_tok) {
+                                const float o = m + bias_f;
+                                C[(size_t)tok * cmap.ld + col] = o;
+                                if (C_copy) C_copy[(size_t)tok * cmap.ld + col] = o;
+                                argmax[(size_t)tok * BN + col] = (uint8_t)am;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int row = ld * 32 + j;                            // compile-time after unrolling
+                            if (row < kTileRows) {
+                                const int u = row % NU, tok = tok0 + row / NU;
+                                const float v = __uint_as_float(r[j]);
+                                if (u == 0 || v > best) { best = v; best_u = u; }   // first maximum wins (torch.max)
+                                if (u == NU - 1 && tok < n_tok) {
+                                    const float o = best + bias_f;
+                                    C[(size_t)tok * cmap.ld + col] = o;
+                                    if (C_copy) C_copy[(size_t)tok * cmap.ld + col] = o;
+                                    argmax[(size_t)tok * BN + col] = (uint8_t)best_u;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                uint32_t ra[32], rb[32];
+                tmem_ld32(taddr, ra);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr + 32, rb);
+                store_feature32(C, cmap, m0, M, col, ra, bias_f, relu, lane);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr + 64, ra);
+                store_feature32(C, cmap, m0 + 32, M, col, rb, bias_f, relu, lane);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr + 96, rb);
+                store_feature32(C, cmap, m0 + 64, M, col, ra, bias_f, relu, lane);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");     // accumulator fully read: hand it back early
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[a]);
+                store_feature32(C, cmap, m0 + 96, M, col, rb, bias_f, relu, lane);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -867,9 +937,9 @@ static int gemm_impl(const float *A, RowMap amap, const float *B, int ldb, const
     if (K / BK <= kMaxResChunks && n_blocks <= dc_sm_count()) {          // K <= 128: weights resident in tensor memory
         int per_col = dc_sm_count() / n_blocks;                          // CTAs per column block
         if (per_col > m_blocks) per_col = m_blocks;
-        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
-        gemm_tf32x3_wtmem_kernel<<<per_col * n_blocks, kThreads, kSmemBytesWTmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
-                                                                                                      (int)M, N, K, relu);
+        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
+        gemm_tf32x3_wtmem_kernel<0><<<per_col * n_blocks, kThreads, kSmemBytesWTmem, dc_cu_stream(stream)>>>(A, amap, B, ldb, bias, C, cmap,
+                                                                                                         (int)M, N, K, relu, nullptr, nullptr);
         DC_LAUNCH_OK();
         return DC_OK;
     }
@@ -952,6 +1022,31 @@ extern "C" int dc_gemm_tf32x3_blocked(const float *A, int lda, int64_t a_rows_pe
                "dc_gemm_tf32x3_blocked: bad block addressing");
     return gemm_impl(A, make_rowmap(lda, a_rows_per_block, a_block_stride), B, ldb, bias, C,
                      make_rowmap(ldc, c_rows_per_block, c_block_stride), M, N, K, relu, stream);
+}
+
+// Unit-embedding layer with the max-pool fused into the epilogue (policy.py:101-127): basic [N*n_units, 128] x W[128,128]^T
+// -> xmax[n*ld_x + c] = max_u(emb[n,u,c]) + b[c] (and xmax_copy), argmax[n*128 + c]; the [N*n_units, 128] embedding is never stored.
+extern "C" int dc_gemm_unit_max(const float *basic, const float *w, const float *bias, float *xmax, float *xmax_copy, int ld_x,
+                                uint8_t *argmax, int64_t n_tokens, int n_units, dc_stream_t stream) {
+    DC_REQUIRE(basic && w && bias && xmax && argmax && n_tokens > 0, DC_EINVAL, "dc_gemm_unit_max: null pointer / empty input");
+    DC_REQUIRE(n_units == 5 || n_units == 16, DC_EUNSUPPORTED, "dc_gemm_unit_max: n_units=%d (5 or 16; 1-unit groups are plain GEMMs)", n_units);
+    DC_REQUIRE(ld_x >= BN && n_tokens * n_units < (1ll << 31) - BM, DC_EINVAL, "dc_gemm_unit_max: bad ld_x / size");
+    DC_REQUIRE(((uintptr_t)basic & 15) == 0 && ((uintptr_t)w & 15) == 0, DC_EINVAL, "dc_gemm_unit_max: pointers must be 16-byte aligned");
+    const int M = (int)(n_tokens * n_units);
+    const int tile_rows = BM - BM % n_units;
+    int grid = (M + tile_rows - 1) / tile_rows;
+    if (grid > dc_sm_count()) grid = dc_sm_count();
+    const RowMap amap = make_rowmap(BN, 0, 0), cmap = make_rowmap(ld_x, 0, 0);
+    cudaStream_t st = dc_cu_stream(stream);
+    if (n_units == 5) {
+        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
+        gemm_tf32x3_wtmem_kernel<5><<<grid, kThreads, kSmemBytesWTmem, st>>>(basic, amap, w, BN, bias, xmax, cmap, M, BN, BN, 0, xmax_copy, argmax);
+    } else {
+        DC_CUDA(cudaFuncSetAttribute(gemm_tf32x3_wtmem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWTmem));
+        gemm_tf32x3_wtmem_kernel<16><<<grid, kThreads, kSmemBytesWTmem, st>>>(basic, amap, w, BN, bias, xmax, cmap, M, BN, BN, 0, xmax_copy, argmax);
+    }
+    DC_LAUNCH_OK();
+    return DC_OK;
 }
 
 extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni, float *dW,

@@ -2,13 +2,13 @@
 
 Forward and backward are explicit chains of C-ABI kernels -- the fp32-accurate tensor-core GEMMs of
 ``csrc/gemm_tf32x3.cu`` for the 128x128 unit embeddings and the bandwidth kernels of ``csrc/encoder.cu`` around them --
-so that every [N, 40, 128] activation crosses HBM once per use: no ``torch.cat`` of the six groups (the GEMMs write and
-read their group's slice of the unit-embedding tensor in place), no dense zeros+scatter+add for the max-pool backward.
+the forward pass never materialises the [N, 40, 128] unit embedding (max-pool in the embedding GEMM's epilogue, target-unit head
+through ``att W_g``); the backward pass builds its gradient once, densely, for the weight- and data-gradient GEMMs.
 """
 import torch
 
 from . import _lib
-from .ops import PROFILE, _f32c, _need_cuda, gemm_wgrad_supported, wait_h2d
+from .ops import PROFILE, _f32c, _need_cuda, gemm_tf32x3, gemm_wgrad_supported, wait_h2d
 
 UNITS = (1, 5, 16, 16, 1, 1)              # allied/enemy heroes, allied/enemy non-heroes, allied/enemy towers
 OFFSETS = (0, 1, 6, 22, 38, 39)
@@ -51,22 +51,31 @@ def _wgrad_workspace(No, Ni, device):
     return ws
 
 
-# The unit embedding has two gradient sources: the target-unit head (rank-1, arrives first in backward) and the max-pool
-# (arrives with the pre-rnn gradient, after the recurrence).  When the embedding was produced by UnitEncoder, TargetUnit
-# does not materialise its [N,40,128] gradient: it parks (dlogits, attention) in the `link` cell the two Functions of one
-# graph share (created by unit_encoder(), carried by the embedding tensor as `_dc_link`) and UnitEncoder.backward writes the
-# sum of both sources in ONE dense pass (dc_unit_grad_assemble).
+# The unit embedding [N, 40, 128] (policy.py:130-131) is never materialised in the forward pass.  Its two consumers are
+#   * the max-pool: fused into the epilogue of the embedding GEMM (dc_gemm_unit_max: max + arg-max per token and channel; the
+#     1-unit groups are plain GEMMs writing their slot of the pre-rnn row; the enemy-tower embedding is not needed at all in
+#     forward because policy.py:127 takes that slot's maximum from the enemy non-heroes);
+#   * the target-unit head, which is linear in it: logits[n,u] = <att[n] W_g, basic[n,u]> + <att[n], b_g>  (TargetUnit below).
+# In backward the embedding's gradient has two sources -- the head (rank-1: dlogits x att, arrives first) and the max-pool
+# routing (arrives with the pre-rnn gradient, after the recurrence): TargetUnit parks (dlogits, attention) in the `link` cell
+# the two Functions of one graph share and UnitEncoder.backward writes the sum of both in ONE dense pass
+# (dc_unit_grad_assemble) that feeds the weight- and data-gradient GEMMs.
 
 
 def _ptr(t, float_offset=0):
     return t.data_ptr() + 4 * float_offset
 
 
+def _ptr6(tensors):
+    return (_lib._c.c_void_p * 6)(*[t.data_ptr() for t in tensors])
+
+
 class UnitEncoder(torch.autograd.Function):
-    """(env, w_e, b_e, w_b, b_b, units x6, W_g x6, b_g x6) -> unit embedding ``[..., 40, 128]`` and the pre-rnn input row
-    ``[..., 896]`` = relu(affine_env(env)) followed by the six group maxima, written in place by the kernels (no cat).
+    """(env, w_e, b_e, w_b, b_b, units x6, W_g x6, b_g x6) -> the pre-rnn input row ``[..., 896]`` = relu(affine_env(env))
+    followed by the six group maxima, written in place by the kernels (no cat, no ``[N, 40, 128]`` embedding).
 
     maxima slot 5 (enemy towers) is a copy of slot 3 (enemy non-heroes): the reference's ``policy.py:127``.
+    ``link`` (a dict) receives the per-group ``basic`` activations and the embedding weights for the target-unit head.
     """
 
     @staticmethod
@@ -85,39 +94,40 @@ class UnitEncoder(torch.autograd.Function):
         units = [_f32c(u.detach()).reshape(N * n, 12) for u, n in zip(units, UNITS)]
         weights = [_f32c(w.detach()) for w in weights]
         biases = [_f32c(b.detach()) for b in biases]
-        ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
         xcat = torch.empty((N, XCAT), dtype=torch.float32, device=dev)
-        argmax = torch.empty((5, N, C), dtype=torch.uint8, device=dev)
+        argmax = torch.zeros((5, N, C), dtype=torch.uint8, device=dev)         # 1-unit groups: the maximum is unit 0
         env2 = _f32c(env.detach()).reshape(N, 3)
         w_e, b_e = _f32c(w_e.detach()), _f32c(b_e.detach())
         wait_h2d(env2)
         with PROFILE.span("env_fwd", 1, 4 * N * (3 + C)):
             _lib.check(lib.dc_env_fwd(env2.data_ptr(), w_e.data_ptr(), b_e.data_ptr(), xcat.data_ptr(), XCAT, N, st), "dc_env_fwd")
         basics = []
-        for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
+        for g, n_u in enumerate(UNITS):
             R = N * n_u
             basic = torch.empty((R, C), dtype=torch.float32, device=dev)
             wait_h2d(units[g])                       # this group's observations may still be in flight over PCIe
             with PROFILE.span("unit_basic_fwd", 1, 4 * R * (12 + C)):
                 _lib.check(lib.dc_unit_basic_fwd(units[g].data_ptr(), w_b.data_ptr(), b_b.data_ptr(), basic.data_ptr(), R, st),
                            "dc_unit_basic_fwd")
-            with PROFILE.span("gemm_tf32x3", 1, 4 * (2 * R * C + C * C)):
-                _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, weights[g].data_ptr(), C, biases[g].data_ptr(),
-                                                      _ptr(ue, off * C), C, n_u, TOK, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
-            if g < 5:
+            if n_u > 1:                               # embedding GEMM with the max-pool in its epilogue
                 copy = _ptr(xcat, 6 * C) if g == 3 else None
-                with PROFILE.span("unit_max_fwd", 1, N * (4 * n_u * C + 4 * C + C)):
-                    _lib.check(lib.dc_unit_max_fwd(_ptr(ue, off * C), TOK, n_u, _ptr(xcat, (g + 1) * C), copy, XCAT,
-                                                   argmax[g].data_ptr(), N, st), "dc_unit_max_fwd")
+                with PROFILE.span("gemm_unit_max", 1, 4 * (R * C + C * C + N * C) + N * C):
+                    _lib.check(lib.dc_gemm_unit_max(basic.data_ptr(), weights[g].data_ptr(), biases[g].data_ptr(),
+                                                    _ptr(xcat, (g + 1) * C), copy, XCAT, argmax[g].data_ptr(), N, n_u, st),
+                               "dc_gemm_unit_max")
+            elif g < 5:                               # one unit: the embedding IS the maximum -> straight into its slot
+                with PROFILE.span("gemm_tf32x3", 1, 4 * (2 * R * C + C * C)):
+                    _lib.check(lib.dc_gemm_tf32x3_blocked(basic.data_ptr(), C, 0, 0, weights[g].data_ptr(), C, biases[g].data_ptr(),
+                                                          _ptr(xcat, (g + 1) * C), XCAT, 0, 0, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
             basics.append(basic)
+        link["basics"], link["weights"], link["biases"] = basics, weights, biases
         ctx.N = N
         ctx.lead = lead
-        ctx.set_materialize_grads(False)               # an absent d_ue must arrive as None, not as 2.7 GB of zeros
         ctx.save_for_backward(argmax, *units, *basics, *weights, env2, xcat)
-        return ue.view(*lead, MAX_UNITS, C), xcat.view(*lead, XCAT)
+        return xcat.view(*lead, XCAT)
 
     @staticmethod
-    def backward(ctx, d_ue, d_xcat):
+    def backward(ctx, d_xcat):
         saved = ctx.saved_tensors
         argmax, units, basics, weights, env2, xcat = saved[0], saved[1:7], saved[7:13], saved[13:19], saved[19], saved[20]
         N = ctx.N
@@ -125,35 +135,19 @@ class UnitEncoder(torch.autograd.Function):
         st = _lib.stream_ptr()
         dev = argmax.device
         pending = ctx.link.pop("pending", None)
-        dw_e = db_e = None
-        d_xm = None                                    # the maxima part of d_xcat, addressed in place (row pitch 896)
-        if d_xcat is not None:
-            d_xcat = _f32c(d_xcat).reshape(N, XCAT)
-            d_xm = _ptr(d_xcat, C)
-            dw_e = torch.empty((C, 3), dtype=torch.float32, device=dev)
-            db_e = torch.empty(C, dtype=torch.float32, device=dev)
-            with PROFILE.span("env_bwd", 2, 4 * N * (2 * C + 3)):
-                _lib.check(lib.dc_env_bwd(d_xcat.data_ptr(), xcat.data_ptr(), XCAT, env2.data_ptr(), dw_e.data_ptr(), db_e.data_ptr(),
-                                          N, _env_workspace(dev).data_ptr(), st), "dc_env_bwd")
-        if d_ue is None:
-            # one dense pass: rank-1 target-unit part (if that head ran) + max-pool routing
-            d_ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
-            dl, att = pending if pending is not None else (None, None)
-            with PROFILE.span("unit_grad_assemble", 1, N * (4 * MAX_UNITS * C + 4 * 6 * C + 5 * C + 4 * C + 4 * MAX_UNITS)):
-                _lib.check(lib.dc_unit_grad_assemble(None if dl is None else dl.data_ptr(), None if att is None else att.data_ptr(),
-                                                     d_xm, XCAT, argmax.data_ptr(),
-                                                     d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
-        else:
-            d_ue = _f32c(d_ue).reshape(N, MAX_UNITS, C)          # modified in place below (sole consumer)
-            if pending is not None:                               # the embedding had another consumer besides the deferred head:
-                dl, att = pending                                 # add the head's rank-1 part instead of losing it
-                d_ue = torch.addcmul(d_ue, dl.unsqueeze(-1), att.unsqueeze(1))
-            if d_xm is not None:
-                for g in range(5):
-                    copy = d_xm + 4 * 5 * C if g == 3 else None
-                    with PROFILE.span("unit_max_bwd", 1):
-                        _lib.check(lib.dc_unit_max_bwd(_ptr(d_ue, OFFSETS[g] * C), TOK, d_xm + 4 * g * C, copy, XCAT,
-                                                       argmax[g].data_ptr(), N, st), "dc_unit_max_bwd")
+        d_xcat = _f32c(d_xcat).reshape(N, XCAT)
+        d_xm = _ptr(d_xcat, C)                         # the maxima part of d_xcat, addressed in place (row pitch 896)
+        dw_e = torch.empty((C, 3), dtype=torch.float32, device=dev)
+        db_e = torch.empty(C, dtype=torch.float32, device=dev)
+        with PROFILE.span("env_bwd", 2, 4 * N * (2 * C + 3)):
+            _lib.check(lib.dc_env_bwd(d_xcat.data_ptr(), xcat.data_ptr(), XCAT, env2.data_ptr(), dw_e.data_ptr(), db_e.data_ptr(),
+                                      N, _env_workspace(dev).data_ptr(), st), "dc_env_bwd")
+        # d(unit embedding) in one dense pass: rank-1 target-unit part (if that head ran) + max-pool routing
+        d_ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
+        dl, att = pending if pending is not None else (None, None)
+        with PROFILE.span("unit_grad_assemble", 1, N * (4 * MAX_UNITS * C + 4 * 6 * C + 5 * C + 4 * C + 4 * MAX_UNITS)):
+            _lib.check(lib.dc_unit_grad_assemble(None if dl is None else dl.data_ptr(), None if att is None else att.data_ptr(),
+                                                 d_xm, XCAT, argmax.data_ptr(), d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
         dw_b = torch.empty((C, 12), dtype=torch.float32, device=dev)
         db_b = torch.empty(C, dtype=torch.float32, device=dev)
         d_basic = torch.empty((N * max(UNITS), C), dtype=torch.float32, device=dev)
@@ -180,53 +174,61 @@ class UnitEncoder(torch.autograd.Function):
         return (None, None, dw_e, db_e, dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
 
 
+QW = 7 * C     # width of the head's token-level operands: six groups x 128 channels + one block carrying the six bias dots
+
+
 class TargetUnit(torch.autograd.Function):
-    """``logits[..., u] = <attention[..., :], unit_embedding[..., u, :]>`` (``policy.py:152-153``)."""
+    """``logits[..., u] = <attention, unit_embedding[..., u, :]>`` (``policy.py:152-153``) WITHOUT the embedding:
+    ``<att, W_g basic_u + b_g> = <att W_g, basic_u> + <att, b_g>``.  One GEMM over tokens produces ``q = att [W_0|..|W_5|b]``
+    ``[N, 896]``, a bandwidth kernel dots it with the stored ``basic`` rows.  Backward: ``s_g = sum_u dlogits_u basic_u`` (same
+    kernel shape), ``d_att = s [W_0|..|W_5|b]^T`` (one GEMM); the gradient towards the embedding weights and ``basic`` goes
+    through the encoder's dense d(embedding) pass (parked in ``link``)."""
 
     @staticmethod
-    def forward(ctx, att, ue, link):
-        _need_cuda(att, ue)
+    def forward(ctx, att, link):
+        _need_cuda(att)
+        basics, weights, biases = link["basics"], link["weights"], link["biases"]
         lead = att.shape[:-1]
         N = att.numel() // C
-        att2, ue2 = _f32c(att.detach()).reshape(N, C), _f32c(ue.detach()).reshape(N, MAX_UNITS, C)
-        logits = torch.empty((N, MAX_UNITS), dtype=torch.float32, device=att.device)
-        with PROFILE.span("target_unit_fwd", 1, 4 * N * (MAX_UNITS * C + C + MAX_UNITS)):
-            _lib.check(_lib.load().dc_target_unit_fwd(att2.data_ptr(), ue2.data_ptr(), logits.data_ptr(), N, _lib.stream_ptr()),
-                       "dc_target_unit_fwd")
-        ctx.save_for_backward(att2, ue2)
-        ctx.shapes = (att.shape, ue.shape)
-        ctx.link = link                                 # not None: the embedding comes from UnitEncoder, defer its gradient
+        att2 = _f32c(att.detach()).reshape(N, C)
+        dev = att2.device
+        bias_block = torch.zeros((C, C), dtype=torch.float32, device=dev)
+        bias_block[:, :6] = torch.stack(biases, dim=1)
+        bm = torch.cat(list(weights) + [bias_block], dim=1)                  # [128, 896]: bm[c, g*128+j] = W_g[c,j], bm[c, 768+g] = b_g[c]
+        q = gemm_tf32x3(att2, bm.t().contiguous())                           # [N, 896] = att [W_0 | ... | W_5 | b]
+        logits = torch.empty((N, MAX_UNITS), dtype=torch.float32, device=dev)
+        with PROFILE.span("target_unit_fwd", 1, 4 * N * (MAX_UNITS * C + QW + MAX_UNITS)):
+            _lib.check(_lib.load().dc_target_unit_q_fwd(q.data_ptr(), QW, _ptr6(basics), logits.data_ptr(), N, _lib.stream_ptr()),
+                       "dc_target_unit_q_fwd")
+        ctx.save_for_backward(att2, bm, *basics)
+        ctx.link = link
+        ctx.att_shape = att.shape
         return logits.view(*lead, MAX_UNITS)
 
     @staticmethod
     def backward(ctx, dlogits):
-        att2, ue2 = ctx.saved_tensors
+        att2, bm = ctx.saved_tensors[:2]
+        basics = ctx.saved_tensors[2:]
         N = att2.shape[0]
         dl = _f32c(dlogits).reshape(N, MAX_UNITS)
-        d_att = torch.empty_like(att2)
-        deferred = ctx.link is not None
-        d_ue = None if deferred else torch.empty_like(ue2)
+        s = torch.empty((N, QW), dtype=torch.float32, device=att2.device)
         with PROFILE.span("target_unit_bwd", 1):       # bytes depend on how many tokens used the head (others are skipped)
-            _lib.check(_lib.load().dc_target_unit_bwd(dl.data_ptr(), att2.data_ptr(), ue2.data_ptr(), d_att.data_ptr(),
-                                                      None if d_ue is None else d_ue.data_ptr(), N, _lib.stream_ptr()),
-                       "dc_target_unit_bwd")
-        if deferred:
-            ctx.link["pending"] = (dl, att2)                    # consumed by UnitEncoder.backward
-            return d_att.view(ctx.shapes[0]), None, None
-        return d_att.view(ctx.shapes[0]), d_ue.view(ctx.shapes[1]), None
+            _lib.check(_lib.load().dc_target_unit_q_bwd(dl.data_ptr(), _ptr6(basics), s.data_ptr(), QW, N, _lib.stream_ptr()),
+                       "dc_target_unit_q_bwd")
+        d_att = gemm_tf32x3(s, bm)                                          # [N, 128] = s [W_0 | ... | W_5 | b]^T
+        ctx.link["pending"] = (dl, att2)                                     # consumed by UnitEncoder.backward
+        return d_att.view(ctx.att_shape), None
 
 
 def unit_encoder(env, w_e, b_e, w_b, b_b, units, weights, biases):
-    """-> (unit embedding ``[..., 40, 128]``, pre-rnn input ``[..., 896]``)."""
+    """-> (``link``: the handle ``target_unit`` needs, pre-rnn input ``[..., 896]``)."""
     link = {}
-    ue, xcat = UnitEncoder.apply(link, env, w_e, b_e, w_b, b_b, *units, *weights, *biases)
-    if ue.requires_grad:
-        ue._dc_link = link                              # lets target_unit() hand its gradient to this encoder's backward
-    return ue, xcat
+    xcat = UnitEncoder.apply(link, env, w_e, b_e, w_b, b_b, *units, *weights, *biases)
+    return link, xcat
 
 
-def target_unit(att, ue):
-    return TargetUnit.apply(att, ue, getattr(ue, "_dc_link", None))
+def target_unit(att, link):
+    return TargetUnit.apply(att, link)
 
 
 __all__ = ["unit_encoder", "target_unit", "gemm_wgrad_supported"]

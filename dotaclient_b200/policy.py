@@ -115,8 +115,8 @@ class Policy(nn.Module):
 
     # ------------------------------------------------------------------ implementation
     def _encode(self, env, groups):
-        """Observation encoders (``policy.py:97-138``) -> (x ``[..., H]``, unit embedding ``[..., 40, 128]``): the explicit
-        kernel chain of ``csrc/encoder.cu`` + tcgen05 GEMMs (no ``torch.cat``, sparse max-pool backward)."""
+        """Observation encoders (``policy.py:97-138``) -> (x ``[..., H]``, encoder handle for the target-unit head): the explicit
+        kernel chain of ``csrc/encoder.cu`` + tcgen05 GEMMs (no ``torch.cat``, no materialised ``[..., 40, 128]`` unit embedding)."""
         layers = [getattr(self, "affine_unit_" + s) for s, _, _ in UNIT_GROUPS]
         unit_embedding, x = encoder_ops.unit_encoder(
             env, self.affine_env.weight, self.affine_env.bias,

@@ -150,6 +150,17 @@ int dc_unit_max_bwd(float *d_emb, int64_t tok_stride, const float *d_xmax, const
 /* d_ue[n,u,c] = dlogits[n,u]*att[n,c] + (u == argmax_g[n,c] ? d_xmax[n,g,c] : 0) in one dense pass (either term may
  * be absent: dlogits == NULL / d_xmax == NULL); argmax is the [5, N, 128] tensor written by dc_unit_max_fwd.
  * dc_target_unit_bwd accepts d_ue == NULL (d_att only) so that the two gradients of the unit embedding are written once. */
+/* Unit-embedding layer with the max-pool fused into the GEMM epilogue (policy.py:101-127): emb = basic[N*n_units,128] W^T is
+ * reduced per token to xmax[n*ld_x + c] = max_u emb[n,u,c] + b[c] (also written to xmax_copy when not NULL, policy.py:127) and
+ * argmax[n*128 + c] (first maximum wins, like torch.max); the embedding itself is never stored.  n_units = 5 or 16. */
+int dc_gemm_unit_max(const float *basic, const float *w, const float *bias, float *xmax, float *xmax_copy, int ld_x,
+                     uint8_t *argmax, int64_t n_tokens, int n_units, dc_stream_t stream);
+/* Target-unit head without the embedding (policy.py:144-153): logits[n,u] = <q[n, g*128 ..], basic_g[n,u,:]> + q[n, 768+g]
+ * with q = att [W_0|...|W_5|b_0..b_5] (ld_q >= 896) and basics[g] = the [N*units_g, 128] basic activations of group g
+ * (units 1,5,16,16,1,1).  Backward: s[n, g*128 + j] = sum_u dlogits[n,u] basic_g[n,u,j], s[n, 768+g] = sum_u dlogits[n,u]
+ * (zeros in 774..895), so that d_att = s [W_0|...|W_5|b]^T is one GEMM. */
+int dc_target_unit_q_fwd(const float *q, int ld_q, const float *const basics[6], float *logits, int64_t N, dc_stream_t stream);
+int dc_target_unit_q_bwd(const float *dlogits, const float *const basics[6], float *s, int ld_s, int64_t N, dc_stream_t stream);
 int dc_unit_grad_assemble(const float *dlogits, const float *att, const float *d_xmax, int ld_dx,
                           const uint8_t *argmax, float *d_ue, int64_t N, dc_stream_t stream);
 int dc_target_unit_fwd(const float *att, const float *ue, float *logits, int64_t N, dc_stream_t stream);
