@@ -622,17 +622,20 @@ def main():
     dominant = max(fam, key=lambda k: fam[k][0])                        # the family with the largest share of the step
     dom_ms, dom_bytes = fam[dominant]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = None                                                      # measured DRAM bytes per step (ncu), if captured for this shape
+    traffic = step_traffic = None                                       # measured DRAM bytes per step (ncu), if captured for this shape
     try:
         with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
             rec = json.load(f).get("%s_%s" % (args.config, cell))
         if rec and (B, S, H) == (CONFIGS[args.config]["batch"], CONFIGS[args.config]["seq_len"], CONFIGS[args.config]["hidden"]):
-            traffic = rec.get(families[dominant][0] if len(families[dominant]) == 1 else "rnn")
+            traffic = rec.get({"gemm_tf32x3": "gemm_fwd_dgrad", "gemm_wgrad": "gemm_wgrad", "rnn_fwd": "rnn"}[families[dominant][0]])
+            step_traffic = rec.get("step_total")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms,
-                "share_of_step": dom_ms / ms_per_step, "peak_source": peak_src,
+                "share_of_step": dom_ms / ms_per_step, "peak_source": peak_src, "step_traffic": step_traffic,
+                "note": "bound/frac are HBM terms (algorithmic bytes); the K = 128 layers of this family also sit at ~0.6 of the tf32 "
+                        "tensor peak because every product is three MMAs (3xTF32) -- DESIGN.md 9.1",
                 "recurrence": recurrence_roofline(cfg, meas, peak), "kernels": table}
     line = {
         "metric": "optimizer_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
