@@ -216,8 +216,11 @@ class ExperienceBatch:
     def __del__(self):
         # a batch that was uploaded (prefetched) but never trained on must not leave its ready-events behind: a later tensor
         # allocated at the same address would otherwise match a stale event
-        for ptr in getattr(self, "_h2d_ptrs", ()):
-            ops.H2D_EVENTS.pop(ptr, None)
+        try:
+            for ptr in getattr(self, "_h2d_ptrs", ()):
+                ops.H2D_EVENTS.pop(ptr, None)
+        except Exception:                       # interpreter shutdown: module globals may already be gone
+            pass
 
     @property
     def seq_len(self):
@@ -902,14 +905,16 @@ class DotaOptimizer:
 
         losses, entropies, grad_norms = [], [], []
         start_optimizing = time.time()
-        for ep in range(self.epochs):                                      # :469
-            self.mq.process_data_events()
-            loss_d, entropy_d, grad_norm_d = self.train(experiences=batch)
-            losses.append(loss_d)
-            entropies.append(entropy_d)
-            grad_norms.append(grad_norm_d)
+        try:
+            for ep in range(self.epochs):                                  # :469
+                self.mq.process_data_events()
+                loss_d, entropy_d, grad_norm_d = self.train(experiences=batch)
+                losses.append(loss_d)
+                entropies.append(entropy_d)
+                grad_norms.append(grad_norm_d)
+        finally:
+            self.use_cuda_graph = graph_setting
         time_optimizing = time.time() - start_optimizing
-        self.use_cuda_graph = graph_setting
 
         losses = self.list_of_dicts_to_dict_of_lists(losses)
         entropies = self.list_of_dicts_to_dict_of_lists(entropies)
