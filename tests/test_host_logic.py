@@ -279,3 +279,29 @@ def test_synthetic_rollout_schema_and_determinism():
     assert (r["actions"]["target_unit"].any(1) == (enum == 2)).all() and (r["actions"]["ability"].any(1) == (enum == 3)).all()
     assert not r["masks"]["target_unit"][:, 0].any()
     assert all(8 <= L <= 48 for L in ragged_lengths(20, 16, 0))
+
+
+# ------------------------------------------------------------------------------------------------ bench / tools host logic
+def test_bench_config_is_identical_in_both_arms_and_names_the_workload():
+    """The driver compares the `config` of `bench.py` and `bench.py --impl reference`: both come from workload_config()."""
+    import bench
+    cfg = dict(bench.CONFIGS["c2"])
+    a = bench.workload_config(cfg, 1, "hbm")
+    b = bench.workload_config(cfg, 1, "cpu")
+    assert a == b and a["batch_per_gpu"] == 256 and a["seq_len"] == 512 and a["hidden"] == 128 and "workload" in a
+    assert bench.workload_config(cfg, 8, "hbm")["global_batch"] == 2048
+    assert bench.algorithmic_rnn_bytes(cfg) == 12.0 * 256 * 512 * 5 * 128            # SURVEY.md 8(d), LSTM: G + 1 = 5
+
+
+def test_kernel_traffic_json_matches_the_committed_ncu_csv(tmp_path):
+    """profiles/kernel_traffic.json (read by bench.py for roofline.traffic) is derived from profiles/r2_ncu_traffic_c2.csv."""
+    import csv
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rec = json.load(open(os.path.join(root, "profiles", "kernel_traffic.json")))["c2_lstm"]
+    total = 0.0
+    for r in csv.reader(open(os.path.join(root, "profiles", "r2_ncu_traffic_c2.csv"))):
+        if len(r) >= 15 and r[0].isdigit() and r[12].startswith("dram__bytes"):
+            total += float(r[14].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[13]]
+    assert abs(total - rec["step_total"]) <= 1e-6 * total
+    assert 30e9 < rec["step_total"] < 40e9 and rec["gemm_fwd_dgrad"] > rec["rnn"] > 1e9
