@@ -473,6 +473,55 @@ def kernel_table(meas, peak):
     return table
 
 
+KERNEL_FAMILIES = {   # label -> (profile-span names, key of profiles/kernel_traffic.json)
+    "tcgen05 3xTF32 GEMM, forward + data gradient (dc_gemm_tf32x3*, dc_gemm_unit_max)": (["gemm_tf32x3", "gemm_unit_max"], "gemm_fwd_dgrad"),
+    "tcgen05 3xTF32 weight-gradient GEMM (dc_gemm_wgrad_tf32x3*, dc_unit_wgrad_routed)": (["gemm_wgrad"], "gemm_wgrad"),
+    "fused unit-encoder data gradient (dc_unit_dgrad_fused: generated d_emb x W_g on tcgen05 3xTF32, ReLU mask + dW_b reduction in the epilogue)":
+        (["unit_dgrad_fused"], "unit_dgrad_fused"),
+    "recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)": (["rnn_fwd", "rnn_bwd"], "rnn"),
+}
+
+
+def measured_peak_tf32():
+    """Dense tf32 tensor peak = half the measured dense bf16 rate (sustained figure: the kernel runs inside a long step)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            rec = json.load(f)
+        return float(rec.get("bf16_tflops_sustained", rec["bf16_tflops"])) / 2.0, "measured bf16 sustained / 2 (MEASURED_PEAKS.json)"
+    except Exception:
+        return 2250.0 / 2.0, "nominal dense bf16 / 2 (B200_PROFILING.md)"
+
+
+def dominant_roofline(table, ms_per_step, tokens, peak, peak_src, traffic_rec):
+    """`roofline` of the kernel family with the largest share of the step (pure function of the per-kernel table, so that it is
+    tested on the CPU against the committed bench line).  HBM families: algorithmic bytes / CUDA-event time against the measured
+    copy bandwidth.  The fused unit-encoder data gradient moves almost no HBM bytes (1 GB per step): its roof is the tensor pipe --
+    2 x 3 (3xTF32) x rows x 128 x 128 flops over its time against the measured dense tf32 rate."""
+    fam = {}
+    for label, (names, _) in KERNEL_FAMILIES.items():
+        fam[label] = (sum(table[n]["ms"] for n in names if n in table), sum(table[n]["bytes"] for n in names if n in table))
+    dominant = max(fam, key=lambda k: fam[k][0])                        # the family with the largest share of the step
+    dom_ms, dom_bytes = fam[dominant]
+    traffic = traffic_rec.get(KERNEL_FAMILIES[dominant][1]) if traffic_rec else None
+    out = {"kernel": dominant, "traffic": traffic, "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms,
+           "share_of_step": dom_ms / ms_per_step if ms_per_step > 0 else 0.0,
+           "step_traffic": traffic_rec.get("step_total") if traffic_rec else None}
+    hbm_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    if KERNEL_FAMILIES[dominant][0] == ["unit_dgrad_fused"]:
+        tpeak, tsrc = measured_peak_tf32()
+        flops = 6.0 * tokens * 40 * 128 * 128                            # 40 unit rows per token, 128 x 128 layer, three tf32 products
+        tflops = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        out.update({"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak, "peak_source": tsrc,
+                    "tensor_flops_per_step": flops, "hbm": {"achieved_GBps": hbm_gbs, "frac": hbm_gbs / peak, "peak": peak},
+                    "note": "tensor-pipe work counts the three tf32 products of the 3xTF32 split; the kernel is bound by neither roof but by "
+                            "its CUDA-core epilogue and pipeline latency (DESIGN.md 9.1); HBM terms of the same launches under `hbm`"})
+    else:
+        out.update({"bound": "hbm", "achieved": hbm_gbs, "peak": peak, "unit": "GB/s", "frac": hbm_gbs / peak, "peak_source": peak_src,
+                    "note": "bound/frac are HBM terms (algorithmic bytes); the K = 128 layers of the GEMM families also sit at ~0.5 of the "
+                            "tf32 tensor peak because every product is three MMAs (3xTF32) -- DESIGN.md 9.1"})
+    return out
+
+
 def recurrence_roofline(cfg, meas, peak):
     """The kernel north_star names: recurrence forward + backward (+ the GAE scan of the prep pass), ALGORITHMIC bytes
     (12*N*(G+1)*H, + 16*N for GAE) over the CUDA-event time of those launches."""
@@ -613,30 +662,16 @@ def main():
     # Per-kernel table (CUDA events on the launching stream, averaged per step) with each kernel's ALGORITHMIC HBM bytes
     # (inputs read once + outputs written once) -> achieved GB/s and fraction of the measured HBM peak.
     table = kernel_table(meas, peak)
-    families = {"tcgen05 3xTF32 GEMM, forward + data gradient (dc_gemm_tf32x3*, dc_gemm_unit_max)": ["gemm_tf32x3", "gemm_unit_max"],
-                "tcgen05 3xTF32 weight-gradient GEMM (dc_gemm_wgrad_tf32x3*)": ["gemm_wgrad"],
-                "recurrence fwd+bwd (dc_rnn_seq_fwd + dc_rnn_seq_bwd)": ["rnn_fwd", "rnn_bwd"]}
-    fam = {}
-    for label, names in families.items():
-        fam[label] = (sum(table[n]["ms"] for n in names if n in table), sum(table[n]["bytes"] for n in names if n in table))
-    dominant = max(fam, key=lambda k: fam[k][0])                        # the family with the largest share of the step
-    dom_ms, dom_bytes = fam[dominant]
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    traffic = step_traffic = None                                       # measured DRAM bytes per step (ncu), if captured for this shape
+    traffic_rec = None                                                  # measured DRAM bytes per step (ncu), if captured for this shape
     try:
-        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
-            rec = json.load(f).get("%s_%s" % (args.config, cell))
-        if rec and (B, S, H) == (CONFIGS[args.config]["batch"], CONFIGS[args.config]["seq_len"], CONFIGS[args.config]["hidden"]):
-            traffic = rec.get({"gemm_tf32x3": "gemm_fwd_dgrad", "gemm_wgrad": "gemm_wgrad", "rnn_fwd": "rnn"}[families[dominant][0]])
-            step_traffic = rec.get("step_total")
+        if (B, S, H) == (CONFIGS[args.config]["batch"], CONFIGS[args.config]["seq_len"], CONFIGS[args.config]["hidden"]):
+            with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+                traffic_rec = json.load(f).get("%s_%s" % (args.config, cell))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes_per_step": dom_bytes, "kernel_ms_per_step": dom_ms,
-                "share_of_step": dom_ms / ms_per_step, "peak_source": peak_src, "step_traffic": step_traffic,
-                "note": "bound/frac are HBM terms (algorithmic bytes); the K = 128 layers of this family also sit at ~0.6 of the tf32 "
-                        "tensor peak because every product is three MMAs (3xTF32) -- DESIGN.md 9.1",
-                "recurrence": recurrence_roofline(cfg, meas, peak), "kernels": table}
+    roofline = dominant_roofline(table, ms_per_step, tokens, peak, peak_src, traffic_rec)
+    roofline["recurrence"] = recurrence_roofline(cfg, meas, peak)
+    roofline["kernels"] = table
     line = {
         "metric": "optimizer_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

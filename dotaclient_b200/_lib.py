@@ -39,6 +39,8 @@ SIGNATURES = {
     "dc_unit_max_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
     "dc_unit_max_bwd": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
     "dc_unit_grad_assemble": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "dc_unit_wgrad_routed": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "dc_unit_dgrad_fused": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
     "dc_gemm_unit_max": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),
     "dc_target_unit_q_fwd": (_i32, [_vp, _i32, _c.c_void_p * 6, _vp, _i64, _vp]),
     "dc_target_unit_q_bwd": (_i32, [_vp, _c.c_void_p * 6, _vp, _i32, _i64, _vp]),

@@ -36,6 +36,9 @@ int dc_sm_count();
 int dc_gemm_tf32x3_splitk(const float *A, int lda, const float *B, int ldb, float *part, int64_t M, int N, int K, int ksplit,
                           bool first_call, cudaStream_t st);
 
+// csrc/encoder.cu: dW_b / db_b (+)= the fixed-order sum of `nblocks` [128][13] partials (library-internal).
+int dc_unit_basic_reduce(const float *partial, int nblocks, float *dw_b, float *db_b, int accumulate, cudaStream_t st);
+
 __device__ __forceinline__ float dc_sigmoid(float x) { return 1.0f / (1.0f + __expf(-x)); }
 // tanh via one exp; abs error ~1e-7, saturates cleanly for |x| large.
 __device__ __forceinline__ float dc_tanh(float x) { return 1.0f - 2.0f / (__expf(2.0f * x) + 1.0f); }

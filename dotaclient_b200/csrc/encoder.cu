@@ -629,6 +629,12 @@ extern "C" int dc_unit_basic_bwd(const float *d_basic, const float *basic, const
     return DC_OK;
 }
 
+int dc_unit_basic_reduce(const float *partial, int nblocks, float *dw_b, float *db_b, int accumulate, cudaStream_t st) {
+    unit_basic_bwd_reduce_kernel<<<(kC * (kIn + 1) + 255) / 256, 256, 0, st>>>(partial, nblocks, dw_b, db_b, accumulate);
+    DC_LAUNCH_OK();
+    return DC_OK;
+}
+
 extern "C" int dc_env_fwd(const float *env, const float *w_e, const float *b_e, float *out, int ld_out, int64_t N,
                           dc_stream_t stream) {
     DC_REQUIRE(env && w_e && b_e && out && N > 0 && ld_out >= kC && ld_out % 4 == 0 && ((uintptr_t)out & 15) == 0, DC_EINVAL,

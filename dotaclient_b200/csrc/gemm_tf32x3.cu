@@ -615,6 +615,412 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tf32x3_wtmem_kernel(const fl
 }
 
 // =================================================================================================
+// Unit-embedding layer, backward DATA path, fused end to end (policy.py:100-127,152-153 backwards).  In the reference's
+// autograd the gradient of the [N, units, 128] embedding is materialised, multiplied by W_g, masked by the ReLU of the
+// `basic` layer and reduced into dW_b / db_b -- four passes over [N*units, 128] tensors.  Here none of them exists in memory:
+//   * PRODUCERS generate the embedding gradient straight into the swizzled shared-memory tiles:
+//       d_emb[(n,u), c] = (argmax[n,c] == u ? d_xmax[n,c] : 0)  +  dlogits[n,u] * att[n,c]
+//     (max-pool routing + the target-unit head's rank-1 part); the sources are one gradient row, one arg-max row and one
+//     attention row per TOKEN, re-read from L1/L2 by the token's units and prefetched into L2 one tile ahead.
+//   * D^T[j][(n,u)] = sum_c W_g^T[j][c] d_emb[(n,u)][c] on the tensor cores exactly as in gemm_tf32x3_wtmem_kernel (W_g^T
+//     resident in tensor memory, 3xTF32), accumulator feature-major.
+//   * EPILOGUE thread = one feature j of the basic layer: it recomputes the ReLU mask of every row from the row's 12 raw unit
+//     features (the same FMA chain as unit_basic_fwd_kernel, bit-identical to the forward value) and accumulates dW_b[j][0..12)
+//     and db_b[j] in registers across ALL of the CTA's tiles; one [128][13] partial per epilogue half per CTA at the end,
+//     summed in a fixed order by the basic layer's reduce kernel.  The raw features of a tile (<= 6 KB, contiguous) arrive in
+//     shared memory by one 1-D bulk copy (cp.async.bulk + mbarrier complete_tx), double-buffered one tile ahead -- broadcast
+//     global loads would expose a DRAM latency per row.
+// HBM traffic: d_xmax + arg-max + att + dlogits + units, about 1/30 of the four dense passes.  The kernel is bound by the
+// epilogue's CUDA-core work (~25 instructions per row and feature), hence 8 epilogue warps (two per tensor-memory lane
+// quadrant, each taking half of a tile's rows) and only 2 producer groups.
+// Roles: warps 0-7 producers (2 groups), warp 8 MMA issuer, warps 9-16 epilogue.
+constexpr int kDGroups = 2;
+constexpr int kDMmaWarp = 4 * kDGroups;
+constexpr int kDIn = 12;                                           // raw features per unit (policy.py:56)
+constexpr int kDUnitsTile = BM * kDIn;                             // floats per staged units tile
+constexpr size_t kSmemBytesDgrad = (size_t)kWStages * kWStageBytes + 1024 + 256 + 2 * kDUnitsTile * sizeof(float);
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {   // 16-byte aligned, multiple of 16
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {          // explicit ld.shared (volatile: stays behind the mbarrier wait)
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// Producer side of one chunk [128 rows x 32 channels] of d_emb, in two steps so that the global loads of a chunk are ONE batch of
+// independent instructions issued two chunks ahead of their use (a first version loaded row by row behind bounds tests: eight
+// dependent round trips to L2 per chunk, 27,000 cycles per tile, profiles/r2_encoder_bwd.md):
+//   demb_fetch  raw sources -> registers.  For the 16- and 5-unit groups a thread owns (token, 16-byte channel slice) pairs: the
+//               token's gradient slice, its 4 arg-max bytes, its attention slice and the dlogits of the pair's units (8 of the
+//               16 / all 5) -- 18 registers for 8 rows of the chunk, instead of 8 finished rows.  Tokens past the end are clamped
+//               for the loads and zeroed in the second step.
+//   demb_store  d_emb rows from the raw registers, hi/lo split, swizzle-128B stores (row r, slice c at r*128 + ((c ^ r%8) << 4)).
+// The 1-unit groups (row == token) keep finished rows (float4 v[8], the mapping of tile_load_k) with clamped, unconditional loads.
+template <int NU>
+struct DembRaw {
+    static constexpr int kP = NU == 16 ? 1 : 2;                   // (token, slice) pairs per thread
+    static constexpr int kU = NU == 16 ? 8 : NU;                  // units of a pair this thread generates
+    float4 d[kP], d2[kP], a[kP];                                  // d2: second gradient source (16-unit form only; else added at fetch)
+    uint32_t am[kP];
+    float g[kP][kU];
+    bool ok[kP];
+};
+template <>
+struct DembRaw<1> {
+    float4 v[8];
+};
+
+template <int NU>
+__device__ __forceinline__ void demb_fetch(DembRaw<NU> &raw, const float *__restrict__ dx, const float *__restrict__ dx2, int ld_dx,
+                                           const uint8_t *__restrict__ argmax, const float *__restrict__ dl, int ld_dl,
+                                           const float *__restrict__ att, int tok0, int n_tok, int k0, int t) {
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (NU == 1) {
+        const int c = t & 7, r0 = t >> 3;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int n = tok0 + r0 + 16 * i;
+            const bool ok = n < n_tok;
+            const size_t nn = (size_t)min(n, n_tok - 1);
+            float4 d = dx != nullptr ? __ldg(reinterpret_cast<const float4 *>(dx + nn * ld_dx + k0) + c) : zero4;
+            if (dx2 != nullptr) {
+                const float4 d2 = __ldg(reinterpret_cast<const float4 *>(dx2 + nn * ld_dx + k0) + c);
+                d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+            }
+            const float4 a4 = dl != nullptr ? __ldg(reinterpret_cast<const float4 *>(att + nn * 128 + k0) + c) : zero4;
+            const float gl = dl != nullptr ? __ldg(dl + nn * ld_dl) : 0.f;
+            raw.v[i] = ok ? make_float4(fmaf(gl, a4.x, d.x), fmaf(gl, a4.y, d.y), fmaf(gl, a4.z, d.z), fmaf(gl, a4.w, d.w)) : zero4;
+        }
+    } else {
+        constexpr int kTileToks = (BM - BM % NU) / NU;
+#pragma unroll
+        for (int k = 0; k < DembRaw<NU>::kP; ++k) {
+            const int p = t + kProducerThreads * k;                // NU == 16: one pair per thread, two threads (unit halves) per pair
+            const int c = p & 7, tokl = NU == 16 ? p >> 4 : p >> 3;
+            const int u0 = NU == 16 ? ((p >> 3) & 1) * 8 : 0;
+            const bool active = tokl < kTileToks;
+            const int n = tok0 + tokl;
+            raw.ok[k] = active && n < n_tok;
+            const size_t nn = (size_t)min(n, n_tok - 1);
+            float4 d = (active && dx != nullptr) ? __ldg(reinterpret_cast<const float4 *>(dx + nn * ld_dx + k0) + c) : zero4;
+            const float4 d2 = (active && dx2 != nullptr) ? __ldg(reinterpret_cast<const float4 *>(dx2 + nn * ld_dx + k0) + c) : zero4;
+            if constexpr (NU == 16) {
+                raw.d2[k] = d2;                                    // added in demb_store: no arithmetic on loaded values here, so that
+            } else {                                               // the fetch never waits for its own loads
+                d.x += d2.x; d.y += d2.y; d.z += d2.z; d.w += d2.w;
+            }
+            raw.d[k] = d;
+            raw.am[k] = (active && dx != nullptr) ? __ldg(reinterpret_cast<const uint32_t *>(argmax + nn * 128 + k0) + c) : 0u;   // 4 arg-max bytes
+            raw.a[k] = (active && dl != nullptr) ? __ldg(reinterpret_cast<const float4 *>(att + nn * 128 + k0) + c) : zero4;
+#pragma unroll
+            for (int j = 0; j < DembRaw<NU>::kU; ++j) raw.g[k][j] = (active && dl != nullptr) ? __ldg(dl + nn * ld_dl + u0 + j) : 0.f;
+        }
+    }
+}
+
+__device__ __forceinline__ void store_hi_lo(unsigned char *dst_hi, unsigned char *dst_lo, int off, float4 o) {
+    float4 hi, lo;
+    hi.x = tf32_rna(o.x); hi.y = tf32_rna(o.y); hi.z = tf32_rna(o.z); hi.w = tf32_rna(o.w);
+    lo.x = o.x - hi.x; lo.y = o.y - hi.y; lo.z = o.z - hi.z; lo.w = o.w - hi.w;
+    *reinterpret_cast<float4 *>(dst_hi + off) = hi;
+    *reinterpret_cast<float4 *>(dst_lo + off) = lo;
+}
+
+template <int NU>
+__device__ __forceinline__ void demb_store(const DembRaw<NU> &raw, unsigned char *dst_hi, unsigned char *dst_lo, int t) {
+    if constexpr (NU == 1) {
+        tile_store_k(raw.v, dst_hi, dst_lo, t);
+    } else {
+        constexpr int kTileRows = BM - BM % NU, kTileToks = kTileRows / NU;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < DembRaw<NU>::kP; ++k) {
+            const int p = t + kProducerThreads * k;
+            const int c = p & 7, tokl = NU == 16 ? p >> 4 : p >> 3;
+            const int u0 = NU == 16 ? ((p >> 3) & 1) * 8 : 0;
+            if (tokl < kTileToks) {
+                float4 d = raw.d[k];
+                if constexpr (NU == 16) { d.x += raw.d2[k].x; d.y += raw.d2[k].y; d.z += raw.d2[k].z; d.w += raw.d2[k].w; }
+                const float4 a = raw.a[k];
+                const uint32_t am = raw.am[k];
+#pragma unroll
+                for (int j = 0; j < DembRaw<NU>::kU; ++j) {
+                    const int u = u0 + j, r = tokl * NU + u;
+                    const float gl = raw.g[k][j];
+                    float4 o;
+                    o.x = fmaf(gl, a.x, (int)(am & 0xffu) == u ? d.x : 0.f);
+                    o.y = fmaf(gl, a.y, (int)((am >> 8) & 0xffu) == u ? d.y : 0.f);
+                    o.z = fmaf(gl, a.z, (int)((am >> 16) & 0xffu) == u ? d.z : 0.f);
+                    o.w = fmaf(gl, a.w, (int)(am >> 24) == u ? d.w : 0.f);
+                    store_hi_lo(dst_hi, dst_lo, r * 128 + ((c ^ (r & 7)) << 4), raw.ok[k] ? o : zero4);
+                }
+            }
+        }
+        if constexpr (kTileRows < BM) {                            // the rows of the MMA tile past the last whole token stay zero
+            if (t < (BM - kTileRows) * 8) {
+                const int r = kTileRows + (t >> 3), c = t & 7;
+                store_hi_lo(dst_hi, dst_lo, r * 128 + ((c ^ (r & 7)) << 4), zero4);
+            }
+        }
+    }
+}
+
+// one 32-row group LD of a tile: accumulator columns [32 LD, 32 LD + 32) -> registers, then per row the recomputed ReLU mask and
+// the rank-1 updates of this thread's dW_b row.  `us` = shared-window address of the tile's raw unit features (all lanes read the same
+// address: broadcast); kFull = every row of the tile exists (the hot path: no per-row bounds test).
+template <int NU, int LD, bool kFull>
+__device__ __forceinline__ void dgrad_rows32(const uint32_t (&r)[32], uint32_t us, int rows_valid, const float (&wb)[kDIn], float bb,
+                                             float2 (&acc2)[kDIn / 2], float &accb) {
+    constexpr int kTileRows = BM - BM % NU;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+        constexpr int row0 = 32 * LD;
+        const int row = row0 + jj;
+        if (row < kTileRows && (kFull || row < rows_valid)) {
+            const uint32_t up = us + row * (kDIn * 4);
+            const float4 u0 = lds128(up), u1 = lds128(up + 16), u2 = lds128(up + 32);
+            float pre = bb;                                        // the forward value of this (row, feature), before the ReLU
+            pre = fmaf(u0.x, wb[0], pre); pre = fmaf(u0.y, wb[1], pre); pre = fmaf(u0.z, wb[2], pre); pre = fmaf(u0.w, wb[3], pre);
+            pre = fmaf(u1.x, wb[4], pre); pre = fmaf(u1.y, wb[5], pre); pre = fmaf(u1.z, wb[6], pre); pre = fmaf(u1.w, wb[7], pre);
+            pre = fmaf(u2.x, wb[8], pre); pre = fmaf(u2.y, wb[9], pre); pre = fmaf(u2.z, wb[10], pre); pre = fmaf(u2.w, wb[11], pre);
+            const float gval = pre > 0.f ? __uint_as_float(r[jj]) : 0.f;
+            const float2 g2 = make_float2(gval, gval);
+            acc2[0] = __ffma2_rn(g2, make_float2(u0.x, u0.y), acc2[0]);
+            acc2[1] = __ffma2_rn(g2, make_float2(u0.z, u0.w), acc2[1]);
+            acc2[2] = __ffma2_rn(g2, make_float2(u1.x, u1.y), acc2[2]);
+            acc2[3] = __ffma2_rn(g2, make_float2(u1.z, u1.w), acc2[3]);
+            acc2[4] = __ffma2_rn(g2, make_float2(u2.x, u2.y), acc2[4]);
+            acc2[5] = __ffma2_rn(g2, make_float2(u2.z, u2.w), acc2[5]);
+            accb += gval;
+        }
+    }
+}
+template <int NU, int LD>
+__device__ __forceinline__ void dgrad_group(uint32_t taddr, uint64_t *acc_empty_bar, bool last, int lane, uint32_t us, int rows_valid,
+                                            const float (&wb)[kDIn], float bb, float2 (&acc2)[kDIn / 2], float &accb) {
+    constexpr int kTileRows = BM - BM % NU;
+    uint32_t r[32];
+    tmem_ld32(taddr + 32 * LD, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (last) {                                                    // this warp's share of the accumulator is read: hand it back early
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty_bar);
+    }
+    if (rows_valid >= kTileRows) dgrad_rows32<NU, LD, true>(r, us, rows_valid, wb, bb, acc2, accb);
+    else dgrad_rows32<NU, LD, false>(r, us, rows_valid, wb, bb, acc2, accb);
+}
+
+template <int NU>
+__global__ void __launch_bounds__(kThreads, 1) unit_dgrad_fused_kernel(const float *__restrict__ dx, const float *__restrict__ dx2, int ld_dx,
+                                                                       const uint8_t *__restrict__ argmax,
+                                                                       const float *__restrict__ dl, int ld_dl,
+                                                                       const float *__restrict__ att,
+                                                                       const float *__restrict__ Wt, const float *__restrict__ units,
+                                                                       const float *__restrict__ w_b, const float *__restrict__ b_b,
+                                                                       int n_tok, float *__restrict__ partial) {
+    constexpr int kTileRows = BM - BM % NU, kTileToks = kTileRows / NU;
+    constexpr int K = BN, k_chunks = K / BK;                      // the embedding layers are 128 x 128
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kWStages * kWStageBytes);
+    uint64_t *full = bars, *empty = bars + kWStages, *acc_full = bars + 2 * kWStages, *acc_empty = bars + 2 * kWStages + 2;
+    uint64_t *w_ready = bars + 2 * kWStages + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kWStages + 5);
+    uint64_t *u_full = bars + 2 * kWStages + 6, *u_empty = bars + 2 * kWStages + 8;            // units staging (2 buffers)
+    float *units_s = reinterpret_cast<float *>(tiles + (size_t)kWStages * kWStageBytes + 256);  // [2][128 * 12]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = n_tok * NU;
+    const int m_blocks = (M + kTileRows - 1) / kTileRows, m_first = blockIdx.x, m_step = gridDim.x;
+    const int n_my_tiles = m_first < m_blocks ? (m_blocks - m_first + m_step - 1) / m_step : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWStages; ++s) { mbar_init(&full[s], kProducerThreads / 32); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8);
+            mbar_init(&u_full[a], 1); mbar_init(&u_empty[a], 8);
+        }
+        mbar_init(w_ready, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kDMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_w_hi = tmem_base + 2 * kAccCols, tmem_w_lo = tmem_w_hi + 128;
+
+    if (warp < kDMmaWarp) {
+        // ===== PRODUCERS =====
+        const int t = threadIdx.x & (kProducerThreads - 1), g = warp >> 2;
+        if (g == 0) {
+            // W_g^T -> TMEM, once: thread = feature j of the basic layer = its TMEM lane
+            const float *wrow = Wt + (size_t)((warp & 3) * 32 + lane) * K;
+            const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+            for (int k0 = 0; k0 < K; k0 += 8) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wrow + k0)), w1 = __ldg(reinterpret_cast<const float4 *>(wrow + k0 + 4));
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                float hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(w[e]); lo[e] = w[e] - hi[e]; }
+                tmem_st8(tmem_w_hi + lane_addr + k0, hi);
+                tmem_st8(tmem_w_lo + lane_addr + k0, lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(w_ready);
+        }
+        // d_emb chunks: running index c = tile_iter * k_chunks + kc; group g takes c == g (mod kDGroups); the RAW sources of two
+        // chunks wait in registers (ping-pong) while earlier chunks are converted and stored
+        const uint32_t total_chunks = (uint32_t)n_my_tiles * k_chunks;
+        DembRaw<NU> ra, rb;
+        auto fetch = [&](uint32_t cc, DembRaw<NU> &raw) {
+            if (cc >= total_chunks) return;
+            const int ti = (int)(cc / k_chunks), kc = (int)(cc % k_chunks);
+            const int tok0 = (m_first + ti * m_step) * kTileToks;
+            if (kc == 0 && ti + 1 < n_my_tiles) {
+                // the sources of this CTA's NEXT tile -> L2 (they are first touched here; the chunk loads then hit L2, not DRAM)
+                const int ntok0 = tok0 + m_step * kTileToks;
+                for (int idx = t; idx < kTileToks * 4; idx += kProducerThreads) {           // 512-byte rows: 4 lines per token
+                    const int n = min(ntok0 + (idx >> 2), n_tok - 1), line = (idx & 3) * 32;
+                    if (dx != nullptr) prefetch_l2(dx + (size_t)n * ld_dx + line);
+                    if (dx2 != nullptr) prefetch_l2(dx2 + (size_t)n * ld_dx + line);
+                    if (dl != nullptr) prefetch_l2(att + (size_t)n * 128 + line);
+                }
+                for (int idx = t; idx < kTileToks; idx += kProducerThreads) {
+                    const int n = min(ntok0 + idx, n_tok - 1);
+                    if (NU > 1 && dx != nullptr) prefetch_l2(argmax + (size_t)n * 128);
+                    if (dl != nullptr) prefetch_l2(dl + (size_t)n * ld_dl);
+                }
+            }
+            demb_fetch<NU>(raw, dx, dx2, ld_dx, argmax, dl, ld_dl, att, tok0, n_tok, kc * BK, t);
+        };
+        auto emit = [&](uint32_t cc, const DembRaw<NU> &raw) {
+            const int stage = cc % kWStages;
+            mbar_wait(&empty[stage], ((cc / kWStages) & 1) ^ 1);
+            unsigned char *st = tiles + (size_t)stage * kWStageBytes;
+            demb_store<NU>(raw, st, st + kTileBytes, t);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+        };
+        fetch(g, ra);
+        fetch(g + kDGroups, rb);
+        for (uint32_t c = g; c < total_chunks; c += 2 * kDGroups) {
+            emit(c, ra);
+            fetch(c + 2 * kDGroups, ra);
+            if (c + kDGroups < total_chunks) {
+                emit(c + kDGroups, rb);
+                fetch(c + 3 * kDGroups, rb);
+            }
+        }
+    } else if (warp == kDMmaWarp) {
+        // ===== MMA ISSUER =====
+        mbar_wait(w_ready, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t c = 0;
+        int it = 0;
+        for (int mb = m_first; mb < m_blocks; mb += m_step, ++it) {
+            const int a = it & 1;
+            mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + a * kAccCols;
+            for (int kc = 0; kc < k_chunks; ++kc, ++c) {
+                const int stage = c % kWStages;
+                mbar_wait(&full[stage], (c / kWStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t xbase = smem_u32(tiles + (size_t)stage * kWStageBytes);
+                    const uint64_t x_hi = make_desc(xbase), x_lo = make_desc(xbase + kTileBytes);
+#pragma unroll
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)(ks * 2);
+                        const uint32_t kcol = kc * BK + ks * 8;
+                        const uint32_t first = (kc | ks) != 0;
+                        umma_tf32_ts(tmem_d, tmem_w_lo + kcol, x_hi + adv, kIdesc, first);
+                        umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_lo + adv, kIdesc, 1u);
+                        umma_tf32_ts(tmem_d, tmem_w_hi + kcol, x_hi + adv, kIdesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kc == k_chunks - 1) umma_commit(&acc_full[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== EPILOGUE =====  thread = feature j of the basic layer; half h of the warps takes rows [64h, 64h + 64) of a tile
+        const int e = warp - (kDMmaWarp + 1), q4 = warp & 3, half = e >> 2;
+        const int col = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const bool stager = e == 0 && lane == 0;                  // the thread that issues the bulk copies of the raw unit features
+        auto stage_units = [&](int j) {                            // tile number j of this CTA -> buffer j & 1
+            const int m0 = (m_first + j * m_step) * kTileRows;
+            const uint32_t bytes = (uint32_t)min(kTileRows, M - m0) * kDIn * 4;   // rows are 48 bytes: always a multiple of 16
+            mbar_expect_tx(&u_full[j & 1], bytes);
+            bulk_g2s(units_s + (j & 1) * kDUnitsTile, units + (size_t)m0 * kDIn, bytes, &u_full[j & 1]);
+        };
+        if (stager) {
+            if (n_my_tiles > 0) stage_units(0);
+            if (n_my_tiles > 1) stage_units(1);
+        }
+        float wb[kDIn];
+#pragma unroll
+        for (int k = 0; k < kDIn; ++k) wb[k] = __ldg(w_b + col * kDIn + k);
+        const float bb = __ldg(b_b + col);
+        float2 acc2[kDIn / 2];                                    // (dW_b[j][2kk], dW_b[j][2kk+1])
+#pragma unroll
+        for (int kk = 0; kk < kDIn / 2; ++kk) acc2[kk] = make_float2(0.f, 0.f);
+        float accb = 0.f;
+        for (int it = 0; it < n_my_tiles; ++it) {
+            const int a = it & 1;
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const int rows_valid = M - (m_first + it * m_step) * kTileRows;
+            const uint32_t us = smem_u32(units_s + a * kDUnitsTile);   // shared-window address of this tile's raw unit features
+            mbar_wait(&u_full[a], ph);                             // this tile's raw unit features have landed
+            mbar_wait(&acc_full[a], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(a * kAccCols);
+            if (half == 0) {
+                dgrad_group<NU, 0>(taddr, &acc_empty[a], false, lane, us, rows_valid, wb, bb, acc2, accb);
+                dgrad_group<NU, 1>(taddr, &acc_empty[a], true, lane, us, rows_valid, wb, bb, acc2, accb);
+            } else {
+                dgrad_group<NU, 2>(taddr, &acc_empty[a], false, lane, us, rows_valid, wb, bb, acc2, accb);
+                dgrad_group<NU, 3>(taddr, &acc_empty[a], true, lane, us, rows_valid, wb, bb, acc2, accb);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&u_empty[a]);               // this warp is done with the staged features
+            if (stager && it + 2 < n_my_tiles) {                   // refill the buffer once all 8 warps have released it
+                mbar_wait(&u_empty[a], ph);
+                stage_units(it + 2);
+            }
+            __syncwarp();
+        }
+        float *prow = partial + ((size_t)(blockIdx.x * 2 + half) * BN + col) * (kDIn + 1);
+#pragma unroll
+        for (int kk = 0; kk < kDIn / 2; ++kk) { prow[2 * kk] = acc2[kk].x; prow[2 * kk + 1] = acc2[kk].y; }
+        prow[kDIn] = accb;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kDMmaWarp) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// =================================================================================================
 // Weight-gradient GEMM:  dW[No, Ni] = dY[T, No]^T * X[T, Ni]   and   db[No] = column sums of dY.
 //
 // The contraction runs over the TOKEN dimension, so both operands are MN-major in memory (features contiguous).
@@ -695,10 +1101,20 @@ constexpr int kThreadsG = (kGMmaWarp + 1) * 32;                     // 544
 constexpr size_t kSmemBytesWgradA = (size_t)kGBStages * 2 * kTileBytes + 1024 + 256 + 2 * 128 * sizeof(float);
 constexpr uint32_t kIdescBMN = kIdesc | (1u << 16);                  // A: TMEM (K-major by construction), B: MN-major shared memory
 
+//
+// NU > 0 ("routed"): dY is not read, it is the max-pool routing of a unit-embedding layer GENERATED in the A producer --
+// row (token n, unit u), feature o:  (argmax[n,o] == u) ? dY[n*ld + o] (+ dY2[n*ld + o]) : 0  with dY/dY2 the [n_tokens, ld]
+// gradients of the group maximum (policy.py:102-127) -- so the dense [n_tokens*NU, 128] gradient never exists in memory.
+// A K-chunk then holds whole tokens: kRPC = (32 / NU) * NU rows (30 for the 5-unit group, the last two rows are zero).
+template <int NU>
 __global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const float *__restrict__ dY, RowMap ymap,
+                                                                        const float *__restrict__ dY2,
+                                                                        const uint8_t *__restrict__ argmax,
                                                                         const float *__restrict__ X, RowMap xmap, int T, int No,
                                                                         int Ni, int nsplit, float *__restrict__ part_w,
                                                                         float *__restrict__ part_b) {
+    constexpr int kTPC = NU > 0 ? BK / NU : 0;                  // tokens per K-chunk (routed form)
+    constexpr int kRPC = NU > 0 ? kTPC * NU : BK;               // rows per K-chunk
     extern __shared__ unsigned char smem_raw[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + (size_t)kGBStages * 2 * kTileBytes);
@@ -711,7 +1127,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const fl
     const int n_blocks = Ni / BN, tiles_mn = (No / BM) * n_blocks;
     const int tile = blockIdx.x % tiles_mn, split = blockIdx.x / tiles_mn;
     const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
-    const int chunks_total = (T + BK - 1) / BK;
+    const int chunks_total = (T + kRPC - 1) / kRPC;
     const int my_chunks = split < chunks_total ? (chunks_total - split + nsplit - 1) / nsplit : 0;   // chunk = split + j*nsplit
 
     if (threadIdx.x == 0) {
@@ -740,17 +1156,34 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const fl
         float va[32], vb[32];
         auto fetch = [&](int j, float (&buf)[32]) {
             if (j >= my_chunks) return;
-            const int t0 = (split + j * nsplit) * BK;
-            // rows t0 .. t0+31 of dY: offset of the first, then a walk (+1 row, block wrap for two-level maps)
-            const float *p = dY + ymap.off(t0) + o;
-            int rem = 0;
-            if (ymap.rpb > 0) { const unsigned n = (unsigned)t0, tq = __umulhi(n, ymap.mul); rem = (int)(n - ((tq + ((n - tq) >> 1)) >> ymap.sh) * (unsigned)ymap.rpb); }
-            const long long wrap = ymap.rpb > 0 ? ymap.bs - (long long)ymap.rpb * ymap.ld : 0;
+            if constexpr (NU > 0) {
+                // whole tokens tok0 .. tok0+kTPC-1: one gradient value and one arg-max byte per token, expanded to NU rows
+                const int tok0 = (split + j * nsplit) * kTPC, n_tok = T / NU;
+                float dv[kTPC];
+                int am[kTPC];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                buf[i] = (t0 + i < T) ? __ldg(p) : 0.f;
-                p += ymap.ld;
-                if (ymap.rpb > 0 && ++rem == ymap.rpb) { rem = 0; p += wrap; }
+                for (int k = 0; k < kTPC; ++k) {
+                    const bool ok = tok0 + k < n_tok;
+                    const size_t at = (size_t)(tok0 + k) * ymap.ld + o;
+                    dv[k] = ok ? __ldg(dY + at) : 0.f;
+                    if (ok && dY2 != nullptr) dv[k] += __ldg(dY2 + at);
+                    am[k] = ok ? (int)__ldg(argmax + (size_t)(tok0 + k) * 128 + o) : 255;      // argmax rows are 128 bytes (No == 128)
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) buf[i] = (i < kRPC && am[i / NU] == i % NU) ? dv[i / NU] : 0.f;
+            } else {
+                const int t0 = (split + j * nsplit) * BK;
+                // rows t0 .. t0+31 of dY: offset of the first, then a walk (+1 row, block wrap for two-level maps)
+                const float *p = dY + ymap.off(t0) + o;
+                int rem = 0;
+                if (ymap.rpb > 0) { const unsigned n = (unsigned)t0, tq = __umulhi(n, ymap.mul); rem = (int)(n - ((tq + ((n - tq) >> 1)) >> ymap.sh) * (unsigned)ymap.rpb); }
+                const long long wrap = ymap.rpb > 0 ? ymap.bs - (long long)ymap.rpb * ymap.ld : 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    buf[i] = (t0 + i < T) ? __ldg(p) : 0.f;
+                    p += ymap.ld;
+                    if (ymap.rpb > 0 && ++rem == ymap.rpb) { rem = 0; p += wrap; }
+                }
             }
         };
         auto emit = [&](int j, const float (&buf)[32]) {
@@ -807,9 +1240,13 @@ __global__ void __launch_bounds__(kThreadsG, 1) gemm_wgrad_atmem_kernel(const fl
         const int gb = (warp - 8) >> 2, t = threadIdx.x & (kProducerThreads - 1);
         float4 v[8], vn[8];
         int j = gb;
-        if (j < my_chunks) tile_load_mn(X, xmap, (split + j * nsplit) * BK, T, n0, t, v);
+        auto load_x = [&](int jj, float4 (&buf)[8]) {              // rows of chunk jj; past its kRPC rows (or T) read as zero
+            const int t0 = (split + jj * nsplit) * kRPC;
+            tile_load_mn(X, xmap, t0, min(T, t0 + kRPC), n0, t, buf);
+        };
+        if (j < my_chunks) load_x(j, v);
         for (; j < my_chunks; j += 2) {
-            if (j + 2 < my_chunks) tile_load_mn(X, xmap, (split + (j + 2) * nsplit) * BK, T, n0, t, vn);
+            if (j + 2 < my_chunks) load_x(j + 2, vn);
             const int stage = j % kGBStages;
             mbar_wait(&b_empty[stage], ((j / kGBStages) & 1) ^ 1);
             unsigned char *st = tiles + (size_t)stage * 2 * kTileBytes;
@@ -995,8 +1432,9 @@ static int wgrad_impl(const float *dY, RowMap ymap, const float *X, RowMap xmap,
     float *part_w = reinterpret_cast<float *>(workspace);
     float *part_b = db ? part_w + (size_t)nsplit * No * Ni : nullptr;
     cudaStream_t st = dc_cu_stream(stream);
-    DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
-    gemm_wgrad_atmem_kernel<<<tiles_mn * nsplit, kThreadsG, kSmemBytesWgradA, st>>>(dY, ymap, X, xmap, (int)T, No, Ni, nsplit, part_w, part_b);
+    DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
+    gemm_wgrad_atmem_kernel<0><<<tiles_mn * nsplit, kThreadsG, kSmemBytesWgradA, st>>>(dY, ymap, nullptr, nullptr, X, xmap, (int)T, No, Ni,
+                                                                                      nsplit, part_w, part_b);
     DC_LAUNCH_OK();
     const int total4 = No * Ni / 4 + (db ? No / 4 : 0);
     wgrad_reduce_kernel<<<(total4 + 31) / 32, 32 * kRedRows, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, ldw, db, accumulate);
@@ -1049,9 +1487,79 @@ extern "C" int dc_gemm_unit_max(const float *basic, const float *w, const float 
     return DC_OK;
 }
 
+// Backward data path of one unit-embedding layer, fused (unit_dgrad_fused_kernel): dW_b[128,12] (+)= G^T units, db_b (+)= colsum G,
+//   G[(n,u), j] = relu'(basic[(n,u), j]) * sum_c ( R[(n,u), c] + dlogits[n*ld_dl + u] * att[n*128 + c] ) W_g[c, j],
+// R = the max-pool routing of (d_xmax (+ d_xmax2), argmax) (d_xmax NULL: no routing, e.g. the enemy-tower layer, policy.py:127);
+// dlogits / att NULL: the target-unit head was not used.  w_t = W_g^T [128,128].  Workspace: dc_unit_basic_bwd_workspace_bytes().
+extern "C" int dc_unit_dgrad_fused(const float *d_xmax, const float *d_xmax2, int ld_dx, const uint8_t *argmax, const float *dlogits,
+                                   int ld_dl, const float *att, const float *w_t, const float *units, const float *w_b,
+                                   const float *b_b, int64_t n_tokens, int n_units, float *dw_b, float *db_b, int accumulate,
+                                   void *workspace, dc_stream_t stream) {
+    DC_REQUIRE(w_t && units && w_b && b_b && dw_b && db_b && workspace && n_tokens > 0, DC_EINVAL, "dc_unit_dgrad_fused: null pointer / empty input");
+    DC_REQUIRE(n_units == 1 || n_units == 5 || n_units == 16, DC_EUNSUPPORTED, "dc_unit_dgrad_fused: n_units=%d (1, 5 or 16)", n_units);
+    DC_REQUIRE((d_xmax == nullptr && d_xmax2 == nullptr) || (d_xmax != nullptr && ld_dx >= BN && ld_dx % 4 == 0), DC_EINVAL,
+               "dc_unit_dgrad_fused: bad d_xmax / ld_dx");
+    DC_REQUIRE(d_xmax == nullptr || n_units == 1 || argmax != nullptr, DC_EINVAL, "dc_unit_dgrad_fused: routing needs the arg-max");
+    DC_REQUIRE((dlogits == nullptr) == (att == nullptr) && (dlogits == nullptr || ld_dl >= n_units), DC_EINVAL,
+               "dc_unit_dgrad_fused: dlogits and att come together");
+    DC_REQUIRE(n_tokens * n_units < (1ll << 31) - BM, DC_EINVAL, "dc_unit_dgrad_fused: too many rows");
+    DC_REQUIRE(((uintptr_t)d_xmax & 15) == 0 && ((uintptr_t)d_xmax2 & 15) == 0 && ((uintptr_t)argmax & 3) == 0 && ((uintptr_t)att & 15) == 0 &&
+                   ((uintptr_t)w_t & 15) == 0 && ((uintptr_t)units & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+               DC_EINVAL, "dc_unit_dgrad_fused: d_xmax, att, w_t, units must be 16-byte aligned (arg-max 4-byte)");
+    const int n_tok = (int)n_tokens;
+    const int tile_rows = BM - BM % n_units;
+    int grid = (int)((n_tokens * n_units + tile_rows - 1) / tile_rows);
+    if (grid > dc_sm_count()) grid = dc_sm_count();
+    float *partial = reinterpret_cast<float *>(workspace);
+    cudaStream_t st = dc_cu_stream(stream);
+#define DC_LAUNCH_DGRAD(NU)                                                                                                          \
+    do {                                                                                                                              \
+        DC_CUDA(cudaFuncSetAttribute(unit_dgrad_fused_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesDgrad)); \
+        unit_dgrad_fused_kernel<NU><<<grid, kThreads, kSmemBytesDgrad, st>>>(d_xmax, d_xmax2, ld_dx, argmax, dlogits, ld_dl, att, w_t,    \
+                                                                            units, w_b, b_b, n_tok, partial);                        \
+    } while (0)
+    if (n_units == 1) DC_LAUNCH_DGRAD(1);
+    else if (n_units == 5) DC_LAUNCH_DGRAD(5);
+    else DC_LAUNCH_DGRAD(16);
+#undef DC_LAUNCH_DGRAD
+    DC_LAUNCH_OK();
+    return dc_unit_basic_reduce(partial, 2 * grid, dw_b, db_b, accumulate, st);     // two epilogue halves per CTA
+}
+
 extern "C" int dc_gemm_wgrad_tf32x3(const float *dY, int ldy, const float *X, int ldx, int64_t T, int No, int Ni, float *dW,
                                     int ldw, float *db, int accumulate, void *workspace, dc_stream_t stream) {
     return wgrad_impl(dY, make_rowmap(ldy, 0, 0), X, make_rowmap(ldx, 0, 0), T, No, Ni, dW, ldw, db, accumulate, workspace, stream);
+}
+
+// Weight gradient of one unit-embedding layer from the gradient of its max-pool (policy.py:101-127), without the dense
+// [n_tokens*n_units, 128] gradient of the embedding: dW[128,128] = R^T basic, db[128] = column sums of R, where
+// R[(n,u), c] = (argmax[n,c] == u) ? d_xmax[n*ld_dx + c] (+ d_xmax2[n*ld_dx + c]) : 0 is generated inside the kernel.
+extern "C" int dc_unit_wgrad_routed(const float *d_xmax, const float *d_xmax2, int ld_dx, const uint8_t *argmax, const float *basic,
+                                    int64_t n_tokens, int n_units, float *dW, float *db, void *workspace, dc_stream_t stream) {
+    DC_REQUIRE(d_xmax && argmax && basic && dW && db && workspace && n_tokens > 0, DC_EINVAL, "dc_unit_wgrad_routed: null pointer / empty input");
+    DC_REQUIRE(n_units == 5 || n_units == 16, DC_EUNSUPPORTED, "dc_unit_wgrad_routed: n_units=%d (5 or 16; a 1-unit group is dc_gemm_wgrad_tf32x3)", n_units);
+    DC_REQUIRE(ld_dx >= BM && n_tokens * n_units < (1ll << 31) - BK, DC_EINVAL, "dc_unit_wgrad_routed: bad ld_dx / size");
+    DC_REQUIRE(((uintptr_t)basic & 15) == 0 && ((uintptr_t)dW & 15) == 0 && ((uintptr_t)db & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+               DC_EINVAL, "dc_unit_wgrad_routed: pointers must be 16-byte aligned");
+    const int No = BM, Ni = BN, nsplit = wgrad_splits(No, Ni);
+    const int T = (int)(n_tokens * n_units);
+    float *part_w = reinterpret_cast<float *>(workspace);
+    float *part_b = part_w + (size_t)nsplit * No * Ni;
+    const RowMap ymap = make_rowmap(ld_dx, 0, 0), xmap = make_rowmap(BN, 0, 0);
+    cudaStream_t st = dc_cu_stream(stream);
+    if (n_units == 5) {
+        DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
+        gemm_wgrad_atmem_kernel<5><<<nsplit, kThreadsG, kSmemBytesWgradA, st>>>(d_xmax, ymap, d_xmax2, argmax, basic, xmap, T, No, Ni, nsplit,
+                                                                                part_w, part_b);
+    } else {
+        DC_CUDA(cudaFuncSetAttribute(gemm_wgrad_atmem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytesWgradA));
+        gemm_wgrad_atmem_kernel<16><<<nsplit, kThreadsG, kSmemBytesWgradA, st>>>(d_xmax, ymap, d_xmax2, argmax, basic, xmap, T, No, Ni, nsplit,
+                                                                                 part_w, part_b);
+    }
+    DC_LAUNCH_OK();
+    wgrad_reduce_kernel<<<(No * Ni / 4 + No / 4 + 31) / 32, 32 * kRedRows, 0, st>>>(part_w, part_b, nsplit, No, Ni, dW, Ni, db, 0);
+    DC_LAUNCH_OK();
+    return DC_OK;
 }
 
 extern "C" int dc_gemm_wgrad_tf32x3_blocked(const float *dY, int ldy, int64_t y_rows_per_block, int64_t y_block_stride,

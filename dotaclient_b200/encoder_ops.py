@@ -2,8 +2,9 @@
 
 Forward and backward are explicit chains of C-ABI kernels -- the fp32-accurate tensor-core GEMMs of
 ``csrc/gemm_tf32x3.cu`` for the 128x128 unit embeddings and the bandwidth kernels of ``csrc/encoder.cu`` around them --
-the forward pass never materialises the [N, 40, 128] unit embedding (max-pool in the embedding GEMM's epilogue, target-unit head
-through ``att W_g``); the backward pass builds its gradient once, densely, for the weight- and data-gradient GEMMs.
+neither pass materialises the [N, 40, 128] unit embedding or its gradient: forward has the max-pool in the embedding GEMM's
+epilogue and the target-unit head through ``att W_g``; backward generates the max-pool routing inside the weight- and
+data-gradient kernels and takes the head's rank-1 share through token-level products.
 """
 import torch
 
@@ -14,7 +15,6 @@ UNITS = (1, 5, 16, 16, 1, 1)              # allied/enemy heroes, allied/enemy no
 OFFSETS = (0, 1, 6, 22, 38, 39)
 MAX_UNITS = 40
 C = 128
-TOK = MAX_UNITS * C                        # floats per token in the unit-embedding tensor
 XCAT = 7 * C                               # pre-rnn input row: env encoding + six group maxima (policy.py:129-136)
 
 _basic_ws = {}
@@ -56,10 +56,14 @@ def _wgrad_workspace(No, Ni, device):
 #     1-unit groups are plain GEMMs writing their slot of the pre-rnn row; the enemy-tower embedding is not needed at all in
 #     forward because policy.py:127 takes that slot's maximum from the enemy non-heroes);
 #   * the target-unit head, which is linear in it: logits[n,u] = <att[n] W_g, basic[n,u]> + <att[n], b_g>  (TargetUnit below).
-# In backward the embedding's gradient has two sources -- the head (rank-1: dlogits x att, arrives first) and the max-pool
-# routing (arrives with the pre-rnn gradient, after the recurrence): TargetUnit parks (dlogits, attention) in the `link` cell
-# the two Functions of one graph share and UnitEncoder.backward writes the sum of both in ONE dense pass
-# (dc_unit_grad_assemble) that feeds the weight- and data-gradient GEMMs.
+# In backward the embedding's gradient d_emb[n,u,:] has two sources -- the head (rank 1: dlogits[n,u] * att[n,:], arrives first) and the
+# max-pool routing R (d_xmax[n,:] to the arg-max unit of every channel; arrives with the pre-rnn gradient, after the recurrence).
+# TargetUnit parks (dlogits, att, s) in the `link` cell the two Functions of one graph share; UnitEncoder.backward then needs no
+# dense [N, 40, 128] tensor at all:
+#   dW_g  = R^T basic_g  (dc_unit_wgrad_routed: R generated in the A producer)  +  att^T s_g   (one token-level GEMM for all groups,
+#           s_g = sum_u dlogits_u basic_u from dc_target_unit_q_bwd; its bias block gives the head's share of db_g)
+#   dW_b += (relu'(.) (R + dlogits x att) W_g)^T units   (dc_unit_dgrad_fused: d_emb generated in the producers, the ReLU mask
+#           recomputed and dW_b reduced in the epilogue) -- d_basic never exists either.
 
 
 def _ptr(t, float_offset=0):
@@ -92,6 +96,7 @@ class UnitEncoder(torch.autograd.Function):
         dev = units[0].device
         w_b, b_b = _f32c(w_b.detach()), _f32c(b_b.detach())
         units = [_f32c(u.detach()).reshape(N * n, 12) for u, n in zip(units, UNITS)]
+        units = [u if u.data_ptr() % 16 == 0 else u.clone() for u in units]   # the backward kernels read whole rows as 3 x 16 bytes
         weights = [_f32c(w.detach()) for w in weights]
         biases = [_f32c(b.detach()) for b in biases]
         xcat = torch.empty((N, XCAT), dtype=torch.float32, device=dev)
@@ -123,54 +128,64 @@ class UnitEncoder(torch.autograd.Function):
         link["basics"], link["weights"], link["biases"] = basics, weights, biases
         ctx.N = N
         ctx.lead = lead
-        ctx.save_for_backward(argmax, *units, *basics, *weights, env2, xcat)
+        ctx.save_for_backward(argmax, *units, *basics, *weights, env2, xcat, w_b, b_b)
         return xcat.view(*lead, XCAT)
 
     @staticmethod
     def backward(ctx, d_xcat):
         saved = ctx.saved_tensors
         argmax, units, basics, weights, env2, xcat = saved[0], saved[1:7], saved[7:13], saved[13:19], saved[19], saved[20]
+        w_b, b_b = saved[21], saved[22]
         N = ctx.N
         lib = _lib.load()
         st = _lib.stream_ptr()
         dev = argmax.device
         pending = ctx.link.pop("pending", None)
         d_xcat = _f32c(d_xcat).reshape(N, XCAT)
-        d_xm = _ptr(d_xcat, C)                         # the maxima part of d_xcat, addressed in place (row pitch 896)
         dw_e = torch.empty((C, 3), dtype=torch.float32, device=dev)
         db_e = torch.empty(C, dtype=torch.float32, device=dev)
         with PROFILE.span("env_bwd", 2, 4 * N * (2 * C + 3)):
             _lib.check(lib.dc_env_bwd(d_xcat.data_ptr(), xcat.data_ptr(), XCAT, env2.data_ptr(), dw_e.data_ptr(), db_e.data_ptr(),
                                       N, _env_workspace(dev).data_ptr(), st), "dc_env_bwd")
-        # d(unit embedding) in one dense pass: rank-1 target-unit part (if that head ran) + max-pool routing
-        d_ue = torch.empty((N, MAX_UNITS, C), dtype=torch.float32, device=dev)
-        dl, att = pending if pending is not None else (None, None)
-        with PROFILE.span("unit_grad_assemble", 1, N * (4 * MAX_UNITS * C + 4 * 6 * C + 5 * C + 4 * C + 4 * MAX_UNITS)):
-            _lib.check(lib.dc_unit_grad_assemble(None if dl is None else dl.data_ptr(), None if att is None else att.data_ptr(),
-                                                 d_xm, XCAT, argmax.data_ptr(), d_ue.data_ptr(), N, st), "dc_unit_grad_assemble")
+        dl = att = s_head = None
+        if pending is not None:
+            dl, att, s_head = pending
         dw_b = torch.empty((C, 12), dtype=torch.float32, device=dev)
         db_b = torch.empty(C, dtype=torch.float32, device=dev)
-        d_basic = torch.empty((N * max(UNITS), C), dtype=torch.float32, device=dev)
+        dw_all = torch.zeros((6, C, C), dtype=torch.float32, device=dev)     # zeros: the enemy-tower layer has no max-pool path
+        db_all = torch.zeros((6, C), dtype=torch.float32, device=dev)
         ws_w = _wgrad_workspace(C, C, dev)
         ws_b = _basic_workspace(dev)
-        dws, dbs = [], []
         for g, (n_u, off) in enumerate(zip(UNITS, OFFSETS)):
             R = N * n_u
-            dw = torch.empty((C, C), dtype=torch.float32, device=dev)
-            db = torch.empty(C, dtype=torch.float32, device=dev)
-            with PROFILE.span("gemm_wgrad", 2, 4 * (2 * R * C + C * C)):        # dW_g = d_emb_g^T basic_g, db_g = colsum(d_emb_g)
-                _lib.check(lib.dc_gemm_wgrad_tf32x3_blocked(_ptr(d_ue, off * C), C, n_u, TOK, basics[g].data_ptr(), C, R, C, C,
-                                                            dw.data_ptr(), C, db.data_ptr(), 0, ws_w.data_ptr(), st),
-                           "dc_gemm_wgrad_tf32x3_blocked")
+            routed = g < 5                                 # policy.py:127: enemy towers never reach the maxima
+            dx = _ptr(d_xcat, (g + 1) * C) if routed else None
+            dx2 = _ptr(d_xcat, 6 * C) if g == 3 else None  # ... their slot was fed from the enemy non-hero maximum
+            if routed and n_u > 1:
+                with PROFILE.span("gemm_wgrad", 2, 4 * (R * C + C * C + N * C) + N * C):   # dW_g = R^T basic_g, db_g = colsum(R)
+                    _lib.check(lib.dc_unit_wgrad_routed(dx, dx2, XCAT, argmax[g].data_ptr(), basics[g].data_ptr(), N, n_u,
+                                                        dw_all[g].data_ptr(), db_all[g].data_ptr(), ws_w.data_ptr(), st),
+                               "dc_unit_wgrad_routed")
+            elif routed:                                   # one unit: the routing is the gradient of the maximum itself
+                with PROFILE.span("gemm_wgrad", 2, 4 * (2 * R * C + C * C)):
+                    _lib.check(lib.dc_gemm_wgrad_tf32x3(dx, XCAT, basics[g].data_ptr(), C, R, C, C, dw_all[g].data_ptr(), C,
+                                                        db_all[g].data_ptr(), 0, ws_w.data_ptr(), st), "dc_gemm_wgrad_tf32x3")
             wt = weights[g].t().contiguous()
-            with PROFILE.span("gemm_tf32x3", 1, 4 * (2 * R * C + C * C)):       # d_basic_g = d_emb_g W_g
-                _lib.check(lib.dc_gemm_tf32x3_blocked(_ptr(d_ue, off * C), C, n_u, TOK, wt.data_ptr(), C, None,
-                                                      d_basic.data_ptr(), C, 0, 0, R, C, C, 0, st), "dc_gemm_tf32x3_blocked")
-            with PROFILE.span("unit_basic_bwd", 2, 4 * R * (2 * C + 12)):    # through the ReLU into W_b, b_b (shared by the six groups)
-                _lib.check(lib.dc_unit_basic_bwd(d_basic.data_ptr(), basics[g].data_ptr(), units[g].data_ptr(), dw_b.data_ptr(),
-                                                 db_b.data_ptr(), R, 1 if g > 0 else 0, ws_b.data_ptr(), st), "dc_unit_basic_bwd")
-            dws.append(dw)
-            dbs.append(db)
+            with PROFILE.span("unit_dgrad_fused", 2, N * (4 * C + C) * (1 if routed else 0) + 4 * R * 12 + (4 * N * (C + n_u) if dl is not None else 0)):
+                _lib.check(lib.dc_unit_dgrad_fused(dx, dx2, XCAT, argmax[g].data_ptr() if (routed and n_u > 1) else None,
+                                                   None if dl is None else _ptr(dl, off), MAX_UNITS, None if att is None else att.data_ptr(),
+                                                   wt.data_ptr(), units[g].data_ptr(), w_b.data_ptr(), b_b.data_ptr(), N, n_u,
+                                                   dw_b.data_ptr(), db_b.data_ptr(), 1 if g > 0 else 0, ws_b.data_ptr(), st),
+                           "dc_unit_dgrad_fused")
+        if dl is not None:
+            # the head's share of every dW_g and db_g in ONE token-level product: att^T [s_0 | ... | s_5 | sum_u dlogits]
+            dw_head = torch.empty((C, QW), dtype=torch.float32, device=dev)
+            with PROFILE.span("gemm_wgrad", 2, 4 * (N * C + N * QW + C * QW)):
+                _lib.check(lib.dc_gemm_wgrad_tf32x3(att.data_ptr(), C, s_head.data_ptr(), QW, N, C, QW, dw_head.data_ptr(), QW, None, 0,
+                                                    _wgrad_workspace(C, QW, dev).data_ptr(), st), "dc_gemm_wgrad_tf32x3")
+            dw_all += dw_head[:, :6 * C].reshape(C, 6, C).permute(1, 0, 2)
+            db_all += dw_head[:, 6 * C:6 * C + 6].t()
+        dws, dbs = list(dw_all.unbind(0)), list(db_all.unbind(0))
         return (None, None, dw_e, db_e, dw_b, db_b) + (None,) * 6 + tuple(dws) + tuple(dbs)
 
 
@@ -181,8 +196,8 @@ class TargetUnit(torch.autograd.Function):
     """``logits[..., u] = <attention, unit_embedding[..., u, :]>`` (``policy.py:152-153``) WITHOUT the embedding:
     ``<att, W_g basic_u + b_g> = <att W_g, basic_u> + <att, b_g>``.  One GEMM over tokens produces ``q = att [W_0|..|W_5|b]``
     ``[N, 896]``, a bandwidth kernel dots it with the stored ``basic`` rows.  Backward: ``s_g = sum_u dlogits_u basic_u`` (same
-    kernel shape), ``d_att = s [W_0|..|W_5|b]^T`` (one GEMM); the gradient towards the embedding weights and ``basic`` goes
-    through the encoder's dense d(embedding) pass (parked in ``link``)."""
+    kernel shape), ``d_att = s [W_0|..|W_5|b]^T`` (one GEMM); the gradient towards the embedding weights and the basic layer
+    is finished by ``UnitEncoder.backward`` from (dlogits, att, s) parked in ``link``."""
 
     @staticmethod
     def forward(ctx, att, link):
@@ -216,7 +231,7 @@ class TargetUnit(torch.autograd.Function):
             _lib.check(_lib.load().dc_target_unit_q_bwd(dl.data_ptr(), _ptr6(basics), s.data_ptr(), QW, N, _lib.stream_ptr()),
                        "dc_target_unit_q_bwd")
         d_att = gemm_tf32x3(s, bm)                                          # [N, 128] = s [W_0 | ... | W_5 | b]^T
-        ctx.link["pending"] = (dl, att2)                                     # consumed by UnitEncoder.backward
+        ctx.link["pending"] = (dl, att2, s)                                  # consumed by UnitEncoder.backward
         return d_att.view(ctx.att_shape), None
 
 

@@ -161,6 +161,25 @@ int dc_gemm_unit_max(const float *basic, const float *w, const float *bias, floa
  * (zeros in 774..895), so that d_att = s [W_0|...|W_5|b]^T is one GEMM. */
 int dc_target_unit_q_fwd(const float *q, int ld_q, const float *const basics[6], float *logits, int64_t N, dc_stream_t stream);
 int dc_target_unit_q_bwd(const float *dlogits, const float *const basics[6], float *s, int ld_s, int64_t N, dc_stream_t stream);
+/* Backward of one unit-embedding layer WITHOUT the dense [N*units, 128] gradient of the embedding (what the reference's autograd
+ * materialises behind policy.py:100-127,152-153).  R[(n,u), c] = (argmax[n*128 + c] == u) ? d_xmax[n*ld_dx + c] (+ d_xmax2[..]) : 0 is
+ * the max-pool routing, generated inside the kernels.
+ *   dc_unit_wgrad_routed  dW[128,128] = R^T basic,  db[128] = column sums of R            (n_units = 5 or 16; a 1-unit group is
+ *                         dc_gemm_wgrad_tf32x3 on d_xmax itself; workspace: dc_gemm_wgrad_workspace_bytes(128, 128))
+ *   dc_unit_dgrad_fused   dW_b[128,12] (+)= G^T units, db_b[128] (+)= column sums of G, with
+ *                         G[(n,u), j] = (basic[(n,u), j] > 0) * sum_c (R[(n,u), c] + dlogits[n*ld_dl + u] att[n*128 + c]) W[c, j]:
+ *                         the whole gradient of the embedding (routing + the target-unit head's rank-1 part) is generated inside
+ *                         the kernel; w_t = W^T [128,128]; the ReLU mask is recomputed from units/w_b/b_b (bit-identical to
+ *                         dc_unit_basic_fwd); dlogits (already offset to the group's first unit) and att [N,128] are NULL when the
+ *                         head was not used; d_xmax NULL = no routing (the enemy-tower layer, policy.py:127).  n_units = 1, 5 or
+ *                         16; units, att, d_xmax 16-byte aligned; workspace: dc_unit_basic_bwd_workspace_bytes().
+ * The head's share of dW / db is a token-level product (att^T s, s from dc_target_unit_q_bwd) the caller adds. */
+int dc_unit_wgrad_routed(const float *d_xmax, const float *d_xmax2, int ld_dx, const uint8_t *argmax, const float *basic,
+                         int64_t n_tokens, int n_units, float *dW, float *db, void *workspace, dc_stream_t stream);
+int dc_unit_dgrad_fused(const float *d_xmax, const float *d_xmax2, int ld_dx, const uint8_t *argmax, const float *dlogits,
+                        int ld_dl, const float *att, const float *w_t, const float *units, const float *w_b,
+                        const float *b_b, int64_t n_tokens, int n_units, float *dw_b, float *db_b, int accumulate,
+                        void *workspace, dc_stream_t stream);
 int dc_unit_grad_assemble(const float *dlogits, const float *att, const float *d_xmax, int ld_dx,
                           const uint8_t *argmax, float *d_ue, int64_t N, dc_stream_t stream);
 int dc_target_unit_fwd(const float *att, const float *ue, float *logits, int64_t N, dc_stream_t stream);

@@ -140,3 +140,60 @@ def test_dense_target_unit_kernels_through_the_c_abi():
     _lib.check(lib.dc_target_unit_bwd(gd.data_ptr(), a.data_ptr(), u.data_ptr(), d_att.data_ptr(), d_ue.data_ptr(), N, _lib.stream_ptr()), "bwd")
     torch.testing.assert_close(d_att.cpu(), torch.einsum("nu,nuc->nc", go, ue), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(d_ue.cpu(), go.unsqueeze(-1) * att.unsqueeze(1), rtol=1e-6, atol=1e-6)
+
+
+def _encoder_check():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "encoder_check.py")
+    spec = importlib.util.spec_from_file_location("encoder_check", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("N,n_u,dx2", [(1, 16, False), (7, 5, False), (130, 16, True), (1000, 5, False), (1001, 16, True)])
+def test_routed_wgrad_through_the_c_abi(N, n_u, dx2):
+    """dc_unit_wgrad_routed: dW = R^T basic, db = colsum R with the max-pool routing R generated inside the kernel
+    (30-row K-chunks of whole tokens for the 5-unit group, ragged last chunk) against the dense fp64 product."""
+    from dotaclient_b200 import _lib
+    ec = _encoder_check()
+    lib, st, dev = _lib.load(), _lib.stream_ptr(), torch.device("cuda", 0)
+    inp, (dW_r, db_r, _, _) = ec.dense_reference(N, n_u, 11 + N, dx2, False)
+    t = {k: v.to(dev).contiguous() for k, v in inp.items()}
+    dW, db = torch.full((128, 128), 7.0, device=dev), torch.full((128,), 7.0, device=dev)
+    ws = torch.empty(int(lib.dc_gemm_wgrad_workspace_bytes(128, 128)), dtype=torch.uint8, device=dev)
+    dx = t["dx"].data_ptr()
+    _lib.check(lib.dc_unit_wgrad_routed(dx + 4 * 256, dx + 4 * 640 if dx2 else None, 896, t["am"].data_ptr(), t["basic"].data_ptr(), N, n_u,
+                                        dW.data_ptr(), db.data_ptr(), ws.data_ptr(), st), "dc_unit_wgrad_routed")
+    torch.testing.assert_close(dW.cpu().double(), dW_r, rtol=1e-4, atol=2e-5 * max(1.0, float(dW_r.abs().max())))
+    torch.testing.assert_close(db.cpu().double(), db_r, rtol=1e-4, atol=2e-5 * max(1.0, float(db_r.abs().max())))
+
+
+@pytest.mark.parametrize("N,n_u,dx2,head,routed", [(1, 1, False, True, True), (7, 5, False, True, True), (130, 16, True, True, True),
+                                                   (1000, 5, False, False, True), (1001, 16, False, True, True),
+                                                   (300, 1, False, True, False), (26, 5, False, True, True)])
+def test_fused_dgrad_through_the_c_abi(N, n_u, dx2, head, routed):
+    """dc_unit_dgrad_fused: dW_b, db_b of the shared basic layer from (d_xmax, argmax, dlogits, att) without d(embedding) or
+    d_basic in memory -- routing and the rank-1 head term generated in the producers, ReLU mask recomputed in the epilogue --
+    against the dense fp64 chain; 125-row tiles for the 5-unit group, tiles split over the two epilogue halves."""
+    from dotaclient_b200 import _lib
+    ec = _encoder_check()
+    lib, st, dev = _lib.load(), _lib.stream_ptr(), torch.device("cuda", 0)
+    inp, (_, _, dwb_r, dbb_r) = ec.dense_reference(N, n_u, 5 + N, dx2, head, routed)
+    t = {k: v.to(dev).contiguous() for k, v in inp.items()}
+    wt = t["W"].t().contiguous()
+    dwb, dbb = torch.full((128, 12), 7.0, device=dev), torch.full((128,), 7.0, device=dev)
+    ws = torch.empty(int(lib.dc_unit_basic_bwd_workspace_bytes()), dtype=torch.uint8, device=dev)
+    dx = t["dx"].data_ptr()
+    args = (dx + 4 * 256 if routed else None, dx + 4 * 640 if dx2 else None, 896, t["am"].data_ptr() if (routed and n_u > 1) else None,
+            t["dl"].data_ptr() + 4 * 3 if head else None, 40, t["att"].data_ptr() if head else None, wt.data_ptr(),
+            t["units"].data_ptr(), t["w_b"].data_ptr(), t["b_b"].data_ptr(), N, n_u, dwb.data_ptr(), dbb.data_ptr())
+    _lib.check(lib.dc_unit_dgrad_fused(*args, 0, ws.data_ptr(), st), "dc_unit_dgrad_fused")
+    tol = dict(rtol=1e-4, atol=2e-5 * max(1.0, float(dwb_r.abs().max())))
+    torch.testing.assert_close(dwb.cpu().double(), dwb_r, **tol)
+    torch.testing.assert_close(dbb.cpu().double(), dbb_r, **tol)
+    _lib.check(lib.dc_unit_dgrad_fused(*args, 1, ws.data_ptr(), st), "dc_unit_dgrad_fused")       # accumulate: twice the gradient
+    torch.testing.assert_close(dwb.cpu().double(), 2 * dwb_r, **tol)
+    # bad arguments are reported, not launched
+    assert lib.dc_unit_dgrad_fused(*args[:12], 3, *args[13:], 0, ws.data_ptr(), st) != 0

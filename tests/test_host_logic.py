@@ -304,4 +304,27 @@ def test_kernel_traffic_json_matches_the_committed_ncu_csv(tmp_path):
         if len(r) >= 15 and r[0].isdigit() and r[12].startswith("dram__bytes"):
             total += float(r[14].replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[r[13]]
     assert abs(total - rec["step_total"]) <= 1e-6 * total
-    assert 30e9 < rec["step_total"] < 40e9 and rec["gemm_fwd_dgrad"] > rec["rnn"] > 1e9
+    assert 15e9 < rec["step_total"] < 25e9 and rec["gemm_fwd_dgrad"] > rec["rnn"] > 1e9     # 35.2 GB before the fused encoder backward
+    assert rec["unit_dgrad_fused"] < 2e9                                                     # ... whose data-gradient kernel moves ~1 GB
+
+
+def test_dominant_roofline_of_the_committed_bench_line():
+    """bench.py's `roofline` names the kernel family with the largest share of the step; checked on the per-kernel table of the
+    committed C2 line (profiles/r2_bench_c2_n1.json): the fused unit-encoder data gradient, bound by the tensor pipe, with
+    its measured DRAM traffic from profiles/kernel_traffic.json; without it the forward/dgrad GEMM family in HBM terms."""
+    import json
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    line = json.loads(open(os.path.join(root, "profiles", "r2_bench_c2_n1.json")).read().strip().splitlines()[-1])
+    rec = json.load(open(os.path.join(root, "profiles", "kernel_traffic.json")))["c2_lstm"]
+    table = line["roofline"]["kernels"]
+    r = bench.dominant_roofline(table, line["ms_per_step"], 256 * 512, 6576.7, "measured", rec)
+    assert "dc_unit_dgrad_fused" in r["kernel"] and r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert abs(r["kernel_ms_per_step"] - table["unit_dgrad_fused"]["ms"]) < 1e-9 and 0.2 < r["share_of_step"] < 0.3
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and 0.1 < r["frac"] < 0.6
+    assert r["traffic"] == rec["unit_dgrad_fused"] and r["step_traffic"] == rec["step_total"]
+    rest = {k: v for k, v in table.items() if k != "unit_dgrad_fused"}
+    r2 = bench.dominant_roofline(rest, line["ms_per_step"], 256 * 512, 6576.7, "measured", None)
+    assert "dc_gemm_tf32x3" in r2["kernel"] and r2["bound"] == "hbm" and r2["unit"] == "GB/s" and r2["traffic"] is None
+    want = (table["gemm_tf32x3"]["bytes"] + table["gemm_unit_max"]["bytes"]) / ((table["gemm_tf32x3"]["ms"] + table["gemm_unit_max"]["ms"]) * 1e-3) / 1e9
+    assert abs(r2["achieved"] - want) < 1e-6 * want and abs(r2["frac"] - want / 6576.7) < 1e-9

@@ -238,3 +238,79 @@ def test_target_unit_head_is_linear_in_the_unit_embedding():
             off += n
         torch.testing.assert_close(torch.cat(logits, dim=1), ref.detach(), rtol=1e-10, atol=1e-10)
         torch.testing.assert_close(d_att, att.grad, rtol=1e-10, atol=1e-10)
+
+
+def test_unit_encoder_backward_without_the_embedding_gradient():
+    """Algebra and index arithmetic behind the fused unit-encoder backward (csrc/gemm_tf32x3.cu: dc_unit_wgrad_routed,
+    dc_unit_dgrad_fused), restated in numpy with the kernels' own tiling -- 125-row tiles / 30-row K-chunks of whole tokens for
+    the 5-unit group -- against torch autograd through the materialised [N,40,128] embedding (policy.py:99-136,144-153):
+      dW_g = R^T basic_g + att^T s_g,  db_g = colsum R + att^T sum_u dlogits,   R = max-pool routing, s_g = sum_u dlogits_u basic_u
+      dW_b = sum_g (relu' . ((R + dlogits x att) W_g))^T units_g."""
+    import torch.nn.functional as F
+    UNITS, OFF, N, BM = (1, 5, 16, 16, 1, 1), (0, 1, 6, 22, 38, 39), 29, 128
+    g = torch.Generator().manual_seed(1)
+    dd = dict(generator=g, dtype=torch.float64)
+    w_b = (torch.randn(128, 12, **dd) * 0.3).requires_grad_(True)
+    b_b = (torch.randn(128, **dd) * 0.1).requires_grad_(True)
+    units = [torch.randn(N, n, 12, **dd) for n in UNITS]
+    W = [(torch.randn(128, 128, **dd) * 0.1).requires_grad_(True) for _ in UNITS]
+    b = [(torch.randn(128, **dd) * 0.1).requires_grad_(True) for _ in UNITS]
+    att = torch.randn(N, 128, **dd)
+    basic = [F.relu(F.linear(u, w_b, b_b)) for u in units]
+    emb = [F.linear(x, w, bb) for x, w, bb in zip(basic, W, b)]
+    mx = [e.max(dim=-2) for e in emb]
+    xm = [m[0] for m in mx]
+    xm[5] = xm[3]                                                  # policy.py:127
+    tu = torch.einsum("nc,nuc->nu", att, torch.cat(emb, dim=-2))
+    g_x, g_tu = torch.randn(N, 768, **dd), torch.randn(N, 40, **dd)
+    g_tu[::2] = 0
+    ((torch.cat(xm, dim=-1) * g_x).sum() + (tu * g_tu).sum()).backward()
+
+    dxm, dl, attn = g_x.numpy(), g_tu.numpy(), att.numpy()
+    dw_b, db_b = np.zeros((128, 12)), np.zeros(128)
+    for gi, (NU, off) in enumerate(zip(UNITS, OFF)):
+        Wg, bas = W[gi].detach().numpy(), basic[gi].detach().numpy().reshape(N * NU, 128)
+        un, am = units[gi].numpy().reshape(N * NU, 12), mx[gi][1].numpy()
+        routed = gi < 5
+        dx = dxm[:, gi * 128:(gi + 1) * 128] + (dxm[:, 640:768] if gi == 3 else 0) if routed else None
+        # --- dc_unit_dgrad_fused: tiles of whole tokens, d_emb generated row by row, mask recomputed from the raw features
+        tile_rows = BM - BM % NU
+        tile_toks = tile_rows // NU
+        for mb in range((N * NU + tile_rows - 1) // tile_rows):
+            tok0, m0 = mb * tile_toks, mb * tile_rows
+            demb = np.zeros((128, 128))
+            for r in range(tile_rows):
+                n, u = tok0 + r // NU, r % NU
+                if n < N:
+                    if routed:
+                        demb[r] = np.where(am[n] == u, dx[n], 0.0) if NU > 1 else dx[n]
+                    demb[r] += dl[n, off + u] * attn[n]
+            acc = demb @ Wg
+            for row in range(min(tile_rows, N * NU - m0)):
+                pre = un[m0 + row] @ w_b.detach().numpy().T + b_b.detach().numpy()
+                gval = np.where(pre > 0, acc[row], 0.0)
+                dw_b += np.outer(gval, un[m0 + row])
+                db_b += gval
+        # --- dc_unit_wgrad_routed: K-chunks of whole tokens (30 rows + 2 zero rows for the 5-unit group)
+        dW, db = np.zeros((128, 128)), np.zeros(128)
+        if routed and NU > 1:
+            tpc = 32 // NU
+            rpc, T = tpc * NU, N * NU
+            for ch in range((T + rpc - 1) // rpc):
+                A, X = np.zeros((32, 128)), np.zeros((32, 128))
+                for i in range(rpc):
+                    n = ch * tpc + i // NU
+                    if n < N:
+                        A[i] = np.where(am[n] == i % NU, dx[n], 0.0)
+                    if ch * rpc + i < min(T, ch * rpc + rpc):
+                        X[i] = bas[ch * rpc + i]
+                dW += A.T @ X
+                db += A.sum(0)
+        elif routed:
+            dW, db = dx.T @ bas, dx.sum(0)
+        s = np.einsum("nu,nuj->nj", dl[:, off:off + NU], bas.reshape(N, NU, 128))       # dc_target_unit_q_bwd
+        dW, db = dW + attn.T @ s, db + attn.T @ dl[:, off:off + NU].sum(1)                # the head's share: one token-level product
+        np.testing.assert_allclose(dW, W[gi].grad.numpy(), rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(db, b[gi].grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(dw_b, w_b.grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(db_b, b_b.grad.numpy(), rtol=1e-9, atol=1e-9)

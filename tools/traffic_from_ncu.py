@@ -14,7 +14,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FAMILY = [("gemm_fwd_dgrad", r"gemm_tf32x3_(wtmem_)?kernel"), ("gemm_wgrad", r"gemm_wgrad_atmem_kernel|wgrad_reduce_kernel"),
-          ("rnn", r"(fwd|bwd)_(resident|cluster|generic)_kernel|(fwd|bwd)_gate_kernel"), ("encoder", r"unit_|target_unit|env_(fwd|bwd)"),
+          ("rnn", r"(fwd|bwd)_(resident|cluster|generic)_kernel|(fwd|bwd)_gate_kernel"), ("unit_dgrad_fused", r"unit_dgrad_fused_kernel"),
+          ("encoder", r"unit_|target_unit|env_(fwd|bwd)"),
           ("ppo_loss", r"ppo_"), ("grad_finish", r"grad_sumsq|adam_kernel|finish_tail|grad_flags")]
 
 
