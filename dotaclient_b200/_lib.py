@@ -32,13 +32,9 @@ SIGNATURES = {
                                             _vp]),
     "dc_unit_basic_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "dc_unit_basic_bwd_workspace_bytes": (_sz, []),
-    "dc_unit_basic_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dc_env_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _vp]),
     "dc_env_bwd_workspace_bytes": (_sz, []),
     "dc_env_bwd": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
-    "dc_unit_max_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _i32, _vp, _i64, _vp]),
-    "dc_unit_max_bwd": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _i64, _vp]),
-    "dc_unit_grad_assemble": (_i32, [_vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "dc_unit_wgrad_routed": (_i32, [_vp, _vp, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "dc_unit_dgrad_fused": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
     "dc_gemm_unit_max": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _i32, _vp]),

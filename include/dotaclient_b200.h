@@ -122,19 +122,12 @@ int dc_gemm_wgrad_tf32x3_blocked(const float *dY, int ldy, int64_t y_rows_per_bl
 /* ---- unit encoder / target-unit head: the bandwidth-bound pieces ------------------------------
  * (policy.py:99-136,144-153; the 128x128 embedding GEMMs themselves are dc_gemm_tf32x3*)
  *   dc_unit_basic_fwd   basic[R,128] = relu(units[R,12] W_b^T + b_b)            policy.py:100,105,...
- *   dc_unit_basic_bwd   dW_b[128,12] (+)= (d_basic * (basic>0))^T units ; db_b[128] (+)= column sums
- *   dc_unit_max_fwd     per token n and channel c: max over `units` rows at emb + n*tok_stride (+ u*128), value to
- *                       xmax[n*ld_x + c] (and to xmax_copy: policy.py:127 feeds the enemy-tower slot from the
- *                       enemy-nonhero max), index to argmax[n*128 + c]           policy.py:102-127
- *   dc_unit_max_bwd     d_emb[n, argmax[n,c], c] += d_xmax[n*ld + c] (+ d_xmax_copy) -- in place, sparse
  *   dc_target_unit_fwd  logits[n,u] = <att[n,:], ue[n,u,:]>, ue = [N,40,128]    policy.py:152-153
  *   dc_target_unit_bwd  d_att[n,:] = sum_u dlogits[n,u] ue[n,u,:];  d_ue[n,u,:] = dlogits[n,u] att[n,:]
  */
 int dc_unit_basic_fwd(const float *units, const float *w_b, const float *b_b, float *basic, int64_t R,
                       dc_stream_t stream);
-size_t dc_unit_basic_bwd_workspace_bytes(void);
-int dc_unit_basic_bwd(const float *d_basic, const float *basic, const float *units, float *dw_b, float *db_b,
-                      int64_t R, int accumulate, void *workspace, dc_stream_t stream);
+size_t dc_unit_basic_bwd_workspace_bytes(void);   /* partial sums of dW_b / db_b: the workspace of dc_unit_dgrad_fused */
 /* Environment encoder (policy.py:55,97): out[n*ld_out + c] = relu(env[n,:3] . W_e[c,:] + b_e[c]), c < 128 -- written into
  * columns [0,128) of the concatenated pre-rnn input row (ld_out = 896), so the reference's torch.cat (policy.py:129-136)
  * is never materialised.  dc_env_bwd: dW_e[128,3] = (d_out * (out>0))^T env, db_e[128] = column sums (deterministic). */
@@ -143,13 +136,6 @@ int dc_env_fwd(const float *env, const float *w_e, const float *b_e, float *out,
 size_t dc_env_bwd_workspace_bytes(void);
 int dc_env_bwd(const float *d_out, const float *out, int ld, const float *env, float *dw_e, float *db_e, int64_t N,
                void *workspace, dc_stream_t stream);
-int dc_unit_max_fwd(const float *emb, int64_t tok_stride, int units, float *xmax, float *xmax_copy, int ld_x,
-                    uint8_t *argmax, int64_t N, dc_stream_t stream);
-int dc_unit_max_bwd(float *d_emb, int64_t tok_stride, const float *d_xmax, const float *d_xmax_copy, int ld_dx,
-                    const uint8_t *argmax, int64_t N, dc_stream_t stream);
-/* d_ue[n,u,c] = dlogits[n,u]*att[n,c] + (u == argmax_g[n,c] ? d_xmax[n,g,c] : 0) in one dense pass (either term may
- * be absent: dlogits == NULL / d_xmax == NULL); argmax is the [5, N, 128] tensor written by dc_unit_max_fwd.
- * dc_target_unit_bwd accepts d_ue == NULL (d_att only) so that the two gradients of the unit embedding are written once. */
 /* Unit-embedding layer with the max-pool fused into the GEMM epilogue (policy.py:101-127): emb = basic[N*n_units,128] W^T is
  * reduced per token to xmax[n*ld_x + c] = max_u emb[n,u,c] + b[c] (also written to xmax_copy when not NULL, policy.py:127) and
  * argmax[n*128 + c] (first maximum wins, like torch.max); the embedding itself is never stored.  n_units = 5 or 16. */
@@ -180,8 +166,6 @@ int dc_unit_dgrad_fused(const float *d_xmax, const float *d_xmax2, int ld_dx, co
                         int ld_dl, const float *att, const float *w_t, const float *units, const float *w_b,
                         const float *b_b, int64_t n_tokens, int n_units, float *dw_b, float *db_b, int accumulate,
                         void *workspace, dc_stream_t stream);
-int dc_unit_grad_assemble(const float *dlogits, const float *att, const float *d_xmax, int ld_dx,
-                          const uint8_t *argmax, float *d_ue, int64_t N, dc_stream_t stream);
 int dc_target_unit_fwd(const float *att, const float *ue, float *logits, int64_t N, dc_stream_t stream);
 int dc_target_unit_bwd(const float *dlogits, const float *att, const float *ue, float *d_att, float *d_ue,
                        int64_t N, dc_stream_t stream);
