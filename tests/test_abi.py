@@ -43,6 +43,17 @@ def test_version_and_argument_errors_without_gpu(lib):
     assert rc == -2
     assert lib.dc_rnn_workspace_bytes(1, 7, 128) == 4 * 128 * 128 * 4
     assert lib.dc_rnn_workspace_bytes(0, 33, 256) == 2 * 2 * 8 * 32 * 256 * 4      # two clusters, ping-pong partials
+    # the fused unit-encoder backward: null pointers / unsupported group sizes / misaligned operands are reported, nothing is launched
+    one = 4096                                       # any non-null, 16-byte aligned "pointer": validation fails before it is used
+    assert lib.dc_unit_wgrad_routed(None, None, 896, one, one, 8, 16, one, one, one, None) == -1 and b"dc_unit_wgrad_routed" in lib.dc_last_error()
+    assert lib.dc_unit_wgrad_routed(one, None, 896, one, one, 8, 3, one, one, one, None) == -2          # 5 or 16 units only
+    assert lib.dc_unit_wgrad_routed(one, None, 64, one, one, 8, 16, one, one, one, None) == -1          # row pitch below 128
+    assert lib.dc_unit_dgrad_fused(one, None, 896, one, None, 40, None, None, one, one, one, 8, 16, one, one, 0, one, None) == -1   # no W^T
+    assert lib.dc_unit_dgrad_fused(one, None, 896, one, None, 40, None, one, one, one, one, 8, 4, one, one, 0, one, None) == -2    # 1, 5 or 16
+    assert lib.dc_unit_dgrad_fused(one, None, 896, None, None, 40, None, one, one, one, one, 8, 16, one, one, 0, one, None) == -1  # routing without arg-max
+    assert lib.dc_unit_dgrad_fused(one, None, 896, one, one, 40, None, one, one, one, one, 8, 16, one, one, 0, one, None) == -1    # dlogits without att
+    assert lib.dc_unit_dgrad_fused(one, None, 896, one, None, 40, None, one, one + 4, one, one, 8, 16, one, one, 0, one, None) == -1   # units misaligned
+    assert b"dc_unit_dgrad_fused" in lib.dc_last_error()
 
 
 def test_sass_is_sm100a_only():
