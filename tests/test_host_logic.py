@@ -328,3 +328,31 @@ def test_dominant_roofline_of_the_committed_bench_line():
     assert "dc_gemm_tf32x3" in r2["kernel"] and r2["bound"] == "hbm" and r2["unit"] == "GB/s" and r2["traffic"] is None
     want = (table["gemm_tf32x3"]["bytes"] + table["gemm_unit_max"]["bytes"]) / ((table["gemm_tf32x3"]["ms"] + table["gemm_unit_max"]["ms"]) * 1e-3) / 1e9
     assert abs(r2["achieved"] - want) < 1e-6 * want and abs(r2["frac"] - want / 6576.7) < 1e-9
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The bench lines kept as evidence under profiles/ (one GPU, 2 / 4 / 8 GPUs, reference arm) have every key of the bench.py
+    contract, name the BASELINE metric, and their derived fields are consistent with each other."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+            "data", "config"}
+    for name, n in (("r2_bench_c2_n1.json", 1), ("r2_bench_c2_n2.json", 2), ("r2_bench_c2_n4.json", 4), ("r2_bench_c4_n8.json", 8)):
+        line = json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
+        assert base | {"roofline", "gpu_launches", "clocks"} <= set(line), (name, base - set(line))
+        assert line["metric"] == "optimizer_steps_per_sec" and line["unit"] == "steps/s" and line["higher_is_better"] is True
+        assert line["n_gpus"] == n and line["scaling"] == "weak" and line["dtype"] == "f32" and line["vs_baseline"] is None
+        assert abs(line["value"] - n * 1000.0 / line["ms_per_step"]) <= 1e-6 * line["value"]
+        assert "workload" in line["config"] and "model" not in line["config"]
+        r = line["roofline"]
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        if "c2" in name:                              # the C4 evidence run skipped the end-to-end leg (--skip-e2e)
+            assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"]) and line["e2e"]["h2d_bytes_per_step"] > 0
+        assert line["gpu_launches"] > 0 and not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        if n == 1:
+            cb = line["cpu_baseline"]
+            assert {"value", "unit", "cores", "kind", "sample"} <= set(cb) and cb["kind"] == "port" and cb["value"] > 0
+            assert set(line["extra_configs"]) == {"c1", "c3", "c4"} and all("ms_per_step" in v for v in line["extra_configs"].values())
+    ref = json.loads(open(os.path.join(root, "profiles", "r2_bench_reference_arm_n1.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and base <= set(ref) and ref["metric"] == "optimizer_steps_per_sec"
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
